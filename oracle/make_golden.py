@@ -1,0 +1,160 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ by running the REAL reference (read-only at /root/reference).
+
+TEST INFRASTRUCTURE ONLY; runs in the build container (CPU).  The reference is Python and
+cannot travel to the GPU box, so its outputs on fixed inputs are committed as fixtures:
+
+  tests/golden/fwd_*.npz      CODONNet.forward of the reference classes (fp32 CPU, and an
+                              fp64 run as the rounding-free truth) on the synthetic
+                              weights/frames of oracle/codon_oracle.py
+  tests/golden/cac_*.npz      CAC_channel / CAC_spatial / ChannelGate / SpatialGate / ResCBAM
+  tests/golden/images/        the bundled Middlebury inputs as read by test.py:116-118
+                              (cv2.imread(path, 0) -> single-channel uint8 PNG), labels and the
+                              authors' x4/x8/x16 outputs (data, not code)
+  tests/golden/metrics.json   EvaluationResults (test.py:148-164, exec'd from source lines) and
+                              ssim_2.ssim_exact on those images
+
+Usage:  python oracle/make_golden.py            (needs /root/reference)
+"""
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("CODON_REFERENCE", "/root/reference")
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, HERE)
+import codon_oracle as orc  # noqa: E402
+
+
+def load_reference(scale):
+    """Import the reference model module for a scale; the three directories reuse module names."""
+    for m in ("CAC_module", "attention", "attention.ResCBAM", "CODON_x4", "CODON_x8", "CODON_x16", "ssim_2"):
+        sys.modules.pop(m, None)
+    d = os.path.join(REF, f"CODON_X{scale}")
+    sys.path.insert(0, d)
+    try:
+        mod = importlib.import_module(f"CODON_x{scale}")
+        cac = importlib.import_module("CAC_module")
+        ssim2 = importlib.import_module("ssim_2")
+        rescbam = importlib.import_module("attention.ResCBAM") if scale in (4, 8) else None
+    finally:
+        sys.path.remove(d)
+    return mod, cac, ssim2, rescbam
+
+
+def reference_rmse_fn():
+    """EvaluationResults cannot be imported (test.py does not import here); exec its source lines."""
+    import math  # noqa: F401  (used by the exec'd source)
+    src = open(os.path.join(REF, "CODON_X4", "test.py"), encoding="utf-8").read().split("\n")
+    body = "\n".join(src[147:164])
+    ns = {"np": np, "math": math}
+    exec(body, ns)
+    return ns["EvaluationResults"]
+
+
+def run_forward(scale, seed, shape, name, frame_seed):
+    mod, _, _, _ = load_reference(scale)
+    sd = orc.synthetic_state_dict(scale, seed)
+    b, h, w = shape
+    x, y = orc.synthetic_frames(b, h, w, frame_seed)
+    torch.manual_seed(0)
+    net = mod.CODONNet().eval()
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out32 = net(x, y)
+        net64 = net.double()
+        out64 = net64(x.double(), y.double())
+    np.savez_compressed(os.path.join(GOLD, f"fwd_{name}.npz"),
+                        scale=scale, seed=seed, frame_seed=frame_seed,
+                        x=x.numpy(), y=y.numpy(), out_fp32=out32.numpy(),
+                        out_fp64=out64.numpy())
+    print(f"fwd_{name}: x{scale} seed {seed} {shape}  residual max "
+          f"{float((out64 - x.double()).abs().max()):.4f}  fp32-vs-fp64 {float((out32.double() - out64).abs().max()):.2e}")
+
+
+def run_image_forward(scale, seed, image, name):
+    import cv2
+    mod, _, _, _ = load_reference(scale)
+    sd = orc.synthetic_state_dict(scale, seed)
+    d = cv2.imread(os.path.join(GOLD, "images", f"depth_x{scale}", image), 0)
+    g = cv2.imread(os.path.join(GOLD, "images", "gray", image), 0)
+    x = torch.from_numpy(d / 255).float()[None, None]
+    y = torch.from_numpy(g / 255).float()[None, None]
+    net = mod.CODONNet().eval()
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out32 = net(x, y)
+    np.savez_compressed(os.path.join(GOLD, f"fwd_{name}.npz"), scale=scale, seed=seed, image=image,
+                        out_fp32=out32.numpy())
+    print(f"fwd_{name}: x{scale} seed {seed} {image} {tuple(x.shape)}")
+
+
+def run_cac():
+    _, cac, _, rescbam = load_reference(4)
+    g = torch.Generator().manual_seed(7)
+    sd = orc.synthetic_state_dict(4, 3)
+    x = torch.randn(2, 128, 21, 27, generator=g)
+    ch = cac.CAC_channel(128).eval()
+    ch.load_state_dict({k[len("attention_c2."):]: v for k, v in sd.items() if k.startswith("attention_c2.")})
+    sp = cac.CAC_spatial().eval()
+    sp.load_state_dict({k[len("attention_s2."):]: v for k, v in sd.items() if k.startswith("attention_s2.")})
+    x64 = torch.randn(2, 64, 19, 23, generator=g)
+    cg = rescbam.ChannelGate(64).eval()
+    cg.load_state_dict({k[len("attention_c5."):]: v for k, v in sd.items() if k.startswith("attention_c5.")})
+    sg = rescbam.SpatialGate().eval()
+    sg.load_state_dict({k[len("attention_s5."):]: v for k, v in sd.items() if k.startswith("attention_s5.")})
+    with torch.no_grad():
+        np.savez_compressed(os.path.join(GOLD, "cac_modules.npz"),
+                            x=x.numpy(), channel=ch(x)[:, :, 0, 0].numpy(), spatial=sp(x).numpy(),
+                            pool=cac.ChannelPool()(x).numpy(),
+                            x64=x64.numpy(), channel_gate=cg(x64).numpy(), spatial_gate=sg(x64).numpy())
+    print("cac_modules done")
+
+
+def copy_images_and_metrics():
+    import cv2
+    rmse_fn = reference_rmse_fn()
+    _, _, ssim2, _ = load_reference(4)
+    names = sorted(os.listdir(os.path.join(REF, "CODON_X4", "input_color")))
+    img_dir = os.path.join(GOLD, "images")
+    for sub in ("gray", "label", "depth_x4", "depth_x8", "depth_x16", "ref_out_x4", "ref_out_x8", "ref_out_x16"):
+        os.makedirs(os.path.join(img_dir, sub), exist_ok=True)
+    metrics = {}
+    for n in names:
+        gray = cv2.imread(os.path.join(REF, "CODON_X4", "input_color", n), 0)      # test.py:118
+        label = cv2.imread(os.path.join(REF, "CODON_X4", "input_label", n), 0)     # test.py:117
+        cv2.imwrite(os.path.join(img_dir, "gray", n), gray, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+        cv2.imwrite(os.path.join(img_dir, "label", n), label, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+        for s in (4, 8, 16):
+            dep = cv2.imread(os.path.join(REF, f"CODON_X{s}", "input_depth", n), 0)   # test.py:116
+            out = cv2.imread(os.path.join(REF, f"CODON_X{s}", "output", n), 0)
+            cv2.imwrite(os.path.join(img_dir, f"depth_x{s}", n), dep, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+            cv2.imwrite(os.path.join(img_dir, f"ref_out_x{s}", n), out, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+            metrics[f"x{s}/{n}"] = {
+                "rmse_out": rmse_fn(label, out), "ssim_out": float(ssim2.ssim_exact(label / 255, out / 255)),
+                "rmse_in": rmse_fn(label, dep), "ssim_in": float(ssim2.ssim_exact(label / 255, dep / 255)),
+            }
+    json.dump(metrics, open(os.path.join(GOLD, "metrics.json"), "w"), indent=1, sort_keys=True)
+    for s in (4, 8, 16):
+        r = np.mean([metrics[f"x{s}/{n}"]["rmse_out"] for n in names])
+        q = np.mean([metrics[f"x{s}/{n}"]["ssim_out"] for n in names])
+        print(f"x{s}: mean RMSE {r:.4f} SSIM {q:.4f}")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    copy_images_and_metrics()
+    run_cac()
+    run_forward(4, 0, (2, 48, 64), "x4_s0_b2_48x64", 1234)
+    run_forward(4, 1, (1, 37, 53), "x4_s1_b1_37x53", 77)
+    run_forward(8, 2, (1, 40, 72), "x8_s2_b1_40x72", 5)
+    run_forward(16, 2, (1, 64, 80), "x16_s2_b1_64x80", 99)
+    run_forward(4, 0, (1, 120, 160), "x4_s0_b1_120x160", 4321)
+    run_image_forward(4, 0, "Tsukuba.png", "x4_s0_tsukuba")
