@@ -1,0 +1,216 @@
+// CAC cross-domain attention (CODON_X4/CAC_module.py; call sites CODON_X4/CODON_x4.py:85-118),
+// three HBM-bound kernels per stage on the NHWC 128-channel feature buffer F = [depth | colour]:
+//
+//   stats : one read of F.  Per pixel max / mean over the 128 channels (ChannelPool,
+//           CAC_module.py:78-81) -> pooled [B,H,W,2]; per 1024-pixel chunk the per-channel sum
+//           and max (avg_pool2d / max_pool2d over the frame, CAC_module.py:43,47) -> partials.
+//           16-byte loads, fp32 accumulation, warp-shuffle reductions.
+//   mlp   : fixed-order reduction of the partials (deterministic, independent of batch and GPU
+//           count), the shared 128->8->64 MLP on avg and max, sum, sigmoid (CAC_module.py:29-35,
+//           59-62) -> s_c [B,64].
+//   apply : s_s = sigmoid(conv5x5(pooled)) (CAC_module.py:88-93) from a shared-memory halo tile,
+//           then F = F * s_c[c % 64] * s_s + E in one pass (CODON_x4.py:88-91,117-118).
+//
+// Algorithmic HBM bytes per pixel per stage (e = bytes per element): stats 128e, apply
+// 128e (F) + 128e (E) + 128e (store) = 512e in total.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace codon {
+namespace {
+
+constexpr int kChunkPx = 1024;   // pixels per stats CTA; fixed so that results are batch-invariant
+
+template <typename T>
+__global__ void __launch_bounds__(256) cac_stats_kernel(const T* __restrict__ F, int HW, int chunks,
+                                                        float* __restrict__ pooled,
+                                                        float* __restrict__ part) {
+  constexpr int V = Act<T>::kVec, LPP = 128 / V, PPW = 32 / LPP, U = 4;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane % LPP, sub = lane / LPP;
+  const int p_begin = chunk * kChunkPx, p_end = min(p_begin + kChunkPx, HW);
+  const T* base = F + (size_t)b * HW * 128;
+  float* pl = pooled + (size_t)b * HW * 2;
+
+  float csum[V], cmax[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { csum[j] = 0.f; cmax[j] = -INFINITY; }
+
+  for (int p0 = p_begin + warp * PPW + sub; p0 < p_end + 8 * PPW * U; p0 += 8 * PPW * U) {
+    // p0 - sub is warp-uniform, so the loop trip count is warp-uniform (shuffles below are safe)
+    if (p0 - sub >= p_end) break;
+    float v[U][V];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * 8 * PPW;
+      ok[u] = p < p_end;
+      if (ok[u]) Act<T>::load(base + (size_t)p * 128 + g * V, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float s = 0.f, m = -INFINITY;
+      if (ok[u]) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          csum[j] += v[u][j];
+          cmax[j] = fmaxf(cmax[j], v[u][j]);
+          s += v[u][j];
+          m = fmaxf(m, v[u][j]);
+        }
+      }
+#pragma unroll
+      for (int o = LPP / 2; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      }
+      if (ok[u] && g == 0) {
+        const int p = p0 + u * 8 * PPW;
+        *reinterpret_cast<float2*>(pl + (size_t)p * 2) = make_float2(m, s * (1.0f / 128.0f));
+      }
+    }
+  }
+
+  __shared__ float rs[8 * PPW][128], rm[8 * PPW][128];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    rs[warp * PPW + sub][g * V + j] = csum[j];
+    rm[warp * PPW + sub][g * V + j] = cmax[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float s = 0.f, m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 8 * PPW; ++r) { s += rs[r][threadIdx.x]; m = fmaxf(m, rm[r][threadIdx.x]); }
+    float* dst = part + ((size_t)(b * chunks + chunk) * 2) * 128;
+    dst[threadIdx.x] = s;
+    dst[128 + threadIdx.x] = m;
+  }
+}
+
+// One CTA per frame, 128 threads.  F channel c (depth 0..63 | colour 64..127) is Fcat channel
+// (c + 64) % 128 (Fcat = [colour | depth], CODON_x4.py:85); w1 is indexed by Fcat channel.
+__global__ void __launch_bounds__(128) cac_mlp_kernel(const float* __restrict__ part, int chunks, int HW,
+                                                      const float* __restrict__ w1,
+                                                      const float* __restrict__ b1,
+                                                      const float* __restrict__ w2,
+                                                      const float* __restrict__ b2,
+                                                      float* __restrict__ sc) {
+  __shared__ float avg[128], mx[128], hid[2][8];
+  const int b = blockIdx.x, t = threadIdx.x;
+  float s = 0.f, m = -INFINITY;
+  const float* src = part + (size_t)b * chunks * 256;
+  for (int c = 0; c < chunks; ++c) {
+    s += src[(size_t)c * 256 + t];
+    m = fmaxf(m, src[(size_t)c * 256 + 128 + t]);
+  }
+  const int fc = (t + 64) & 127;
+  avg[fc] = s / (float)HW;
+  mx[fc] = m;
+  __syncthreads();
+  if (t < 16) {
+    const int h = t & 7;
+    const float* v = (t < 8) ? avg : mx;
+    float a = b1[h];
+    for (int j = 0; j < 128; ++j) a = fmaf(w1[h * 128 + j], v[j], a);
+    hid[t >> 3][h] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  if (t < 64) {
+    float za = b2[t], zm = b2[t];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      za = fmaf(w2[t * 8 + h], hid[0][h], za);
+      zm = fmaf(w2[t * 8 + h], hid[1][h], zm);
+    }
+    sc[b * 64 + t] = sigmoidf_exact(za + zm);
+  }
+}
+
+constexpr int kATH = 8, kATW = 32;   // apply tile: 256 pixels
+
+template <typename T>
+__global__ void __launch_bounds__(256) cac_apply_kernel(T* __restrict__ F, const T* __restrict__ E,
+                                                        const float* __restrict__ pooled,
+                                                        const float* __restrict__ sc,
+                                                        const float* __restrict__ ws, int H, int W,
+                                                        int tiles_x) {
+  constexpr int V = Act<T>::kVec, LPP = 128 / V, PH = kATH + 4, PW = kATW + 4;
+  __shared__ float2 sp[PH][PW];
+  __shared__ float sw[50], ssc[64], sss[kATH * kATW];
+  const int b = blockIdx.y, t = threadIdx.x;
+  const int ty0 = (blockIdx.x / tiles_x) * kATH, tx0 = (blockIdx.x % tiles_x) * kATW;
+  const size_t fb = (size_t)b * H * W;
+  if (t < 50) sw[t] = ws[t];
+  if (t >= 64 && t < 128) ssc[t - 64] = sc[b * 64 + t - 64];
+  for (int i = t; i < PH * PW; i += 256) {
+    const int gy = ty0 + i / PW - 2, gx = tx0 + i % PW - 2;
+    float2 v = make_float2(0.f, 0.f);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = __ldg(reinterpret_cast<const float2*>(pooled + (fb + (size_t)gy * W + gx) * 2));
+    sp[i / PW][i % PW] = v;
+  }
+  __syncthreads();
+  {
+    const int r = t / kATW, c = t % kATW;
+    float q = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 5; ++dx) {
+        const float2 pv = sp[r + dy][c + dx];
+        q = fmaf(sw[dy * 5 + dx], pv.x, q);
+        q = fmaf(sw[25 + dy * 5 + dx], pv.y, q);
+      }
+    sss[t] = sigmoidf_exact(q);
+  }
+  __syncthreads();
+#pragma unroll 2
+  for (int i = t; i < kATH * kATW * LPP; i += 256) {
+    const int g = i % LPP, px = i / LPP;
+    const int gy = ty0 + px / kATW, gx = tx0 + px % kATW;
+    if (gy < H && gx < W) {
+      const size_t o = (fb + (size_t)gy * W + gx) * 128 + g * V;
+      float f[V], e[V];
+      Act<T>::load(F + o, f);
+      Act<T>::load(E + o, e);
+      const float s = sss[px];
+      const int c0 = (g * V) & 63;
+#pragma unroll
+      for (int j = 0; j < V; ++j) f[j] = fmaf(f[j], ssc[c0 + j] * s, e[j]);
+      Act<T>::store(F + o, f);
+    }
+  }
+}
+
+}  // namespace
+
+int cac_stats_chunks(int /*B*/, int H, int W) { return cdiv(H * W, kChunkPx); }
+
+cudaError_t launch_cac_stats(const void* F, int act, int B, int H, int W, float* pooled, float* part,
+                             int chunks, cudaStream_t st) {
+  dim3 grid(chunks, B);
+  const int HW = H * W;
+  if (act == ACT_F32) cac_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)F, HW, chunks, pooled, part);
+  else if (act == ACT_BF16) cac_stats_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)F, HW, chunks, pooled, part);
+  else cac_stats_kernel<__half><<<grid, 256, 0, st>>>((const __half*)F, HW, chunks, pooled, part);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const float* w1, const float* b1,
+                           const float* w2, const float* b2, float* sc, cudaStream_t st) {
+  cac_mlp_kernel<<<B, 128, 0, st>>>(part, chunks, HW, w1, b1, w2, b2, sc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* pooled, const float* sc,
+                             const float* ws, int B, int H, int W, cudaStream_t st) {
+  const int tiles_x = cdiv(W, kATW);
+  dim3 grid(tiles_x * cdiv(H, kATH), B);
+  if (act == ACT_F32) cac_apply_kernel<float><<<grid, 256, 0, st>>>((float*)F, (const float*)E, pooled, sc, ws, H, W, tiles_x);
+  else if (act == ACT_BF16) cac_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)F, (const __nv_bfloat16*)E, pooled, sc, ws, H, W, tiles_x);
+  else cac_apply_kernel<__half><<<grid, 256, 0, st>>>((__half*)F, (const __half*)E, pooled, sc, ws, H, W, tiles_x);
+  return cudaGetLastError();
+}
+
+}  // namespace codon

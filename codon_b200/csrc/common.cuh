@@ -1,0 +1,79 @@
+// Shared device/host helpers for libcodon_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace codon {
+
+// Activation element types stored in HBM (NHWC): float (FP32/TF32 modes), bf16, fp16.
+enum ActType : int { ACT_F32 = 0, ACT_BF16 = 1, ACT_F16 = 2 };
+
+__host__ __device__ inline int act_bytes(int t) { return t == ACT_F32 ? 4 : 2; }
+
+template <typename T> struct Act;
+template <> struct Act<float> {
+  static constexpr int kVec = 4;  // elements per 16-byte vector
+  __device__ static inline void load(const float* p, float (&v)[4]) {
+    float4 r = *reinterpret_cast<const float4*>(p);
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+  }
+  __device__ static inline void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __device__ static inline float to_float(float v) { return v; }
+  __device__ static inline float from_float(float v) { return v; }
+};
+template <> struct Act<__nv_bfloat16> {
+  static constexpr int kVec = 8;
+  __device__ static inline void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static inline void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ static inline float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static inline __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
+};
+template <> struct Act<__half> {
+  static constexpr int kVec = 8;
+  __device__ static inline void load(const __half* p, float (&v)[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ static inline void store(__half* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ static inline float to_float(__half v) { return __half2float(v); }
+  __device__ static inline __half from_float(float v) { return __float2half_rn(v); }
+};
+
+__device__ __forceinline__ float sigmoidf_exact(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace codon

@@ -1,0 +1,562 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (BF16, FP16 and TF32 modes).
+//
+// Implements the trunk convolutions of CODONNet (CODON_X4/CODON_x4.py:25-46, call sites :69-84,
+// :120-129): NHWC activations, stride 1, zero padding, no bias; ReLU and the residual add are
+// fused into the epilogue, and the 3x3 || 5x5 multi-scale pair that the reference concatenates
+// (:75-80, :123-125) is ONE launch that writes the 128-channel concat directly.
+//
+// GEMM view: M = pixels, N = output channels (64 or 128), K = taps x input channels.
+//   * A (activations): a CTA owns a tile of 16 x (8*NACC) pixels.  For every 128-byte channel
+//     slab and every horizontal tap offset dx, ONE 4-D TMA box {slab, 16 px, 8*NACC + ks - 1 rows}
+//     lands a halo patch in shared memory (SWIZZLE_128B, one pixel = one 128-B row; out-of-image
+//     pixels are zero-filled by TMA, which is exactly the layer's zero padding).  The ks vertical
+//     taps dy and the NACC 128-pixel sub-tiles then address that one patch through UMMA
+//     descriptors offset by whole 2-KB image rows (1024-B aligned, so the swizzle phase is
+//     unchanged).  A traffic is therefore ~(1 + (ks-1)/(8*NACC)) x ks patches per tile instead of
+//     ks*ks im2col tiles per sub-tile.
+//   * B (weights): host-packed per (slab, tap) K-major blocks already in the SWIZZLE_128B image,
+//     fetched with cp.async.bulk into a 4-deep ring; each block is reused by NACC MMAs groups.
+//   * D: NACC accumulators of 128 lanes x N fp32 columns in TMEM; double-buffered across tiles
+//     when 2*NACC*N <= 512 so the epilogue of tile i overlaps the main loop of tile i+1.
+//   * Roles (192 threads): warp 0 = TMA/bulk producer (one lane), warp 1 = TMEM owner + MMA issuer
+//     (one lane, tcgen05.mma.cta_group::1 M=128), warps 2..5 = epilogue (tcgen05.ld 32x32b ->
+//     ReLU / residual / convert -> 16-byte global stores).  mbarrier pipelines throughout;
+//     persistent CTAs stride over the tile list.
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include "common.cuh"
+#include "kernels.h"
+#include "conv_tc.h"
+
+namespace codon {
+
+namespace {
+
+constexpr int kBStages = 4;
+constexpr uint32_t kBStageBytes = 128 * 128;   // up to 128 rows x 128 B
+constexpr int kThreads = 192;
+
+struct TcKParams {
+  TcJob job[2];
+  int njobs, B, H, W, tiles_x, tiles_y, tiles_per_job, total_tiles;
+  int nslab, slab_elems, ks, pad, ndx, ndy;
+  int dx_ord[kTcMaxTaps], dy_ord[kTcMaxTaps];
+  uint32_t b_bytes[kTcMaxTaps][kTcMaxTaps], b_off[kTcMaxTaps][kTcMaxTaps];
+  uint32_t slab_bytes;
+  int n_cols;
+  uint32_t idesc_full, idesc_half;
+  int relu, out_act, is_tf32, nbuf;
+  uint32_t patch_tx;
+};
+
+template <int NACC> struct TcCfg {
+  static constexpr int kPatchRowsMax = NACC * kTcRowsPerAcc + 4;
+  static constexpr uint32_t kPatchBytes = kPatchRowsMax * kTcTileW * 128;
+  static constexpr int kPatchStages = NACC == 4 ? 2 : (NACC == 2 ? 3 : 4);
+  static constexpr uint32_t kSmemBytes = kPatchStages * kPatchBytes + kBStages * kBStageBytes + 1024 + 256;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    // watchdog: a protocol bug must fault, never hang the GPU
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000LL) {
+      printf("conv_tc: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;              // leading byte offset (unused for swizzled K-major), 16 B units
+  d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Tile { int job, n, y0, x0; };
+__device__ __forceinline__ Tile decode_tile(const TcKParams& p, int t, int tile_h) {
+  Tile r;
+  r.job = t / p.tiles_per_job;
+  int q = t - r.job * p.tiles_per_job;
+  const int per_frame = p.tiles_x * p.tiles_y;
+  r.n = q / per_frame;
+  q -= r.n * per_frame;
+  r.y0 = (q / p.tiles_x) * tile_h;
+  r.x0 = (q % p.tiles_x) * kTcTileW;
+  return r;
+}
+
+// Epilogue of one 32-channel chunk held by one thread (one pixel).
+template <typename T>
+__device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], const TcJob& job, size_t pix, int c0,
+                                            bool relu) {
+  constexpr int V = Act<T>::kVec;
+  T* out = static_cast<T*>(job.out) + pix * job.out_stride + job.out_off + c0;
+  const T* res = job.res ? static_cast<const T*>(job.res) + pix * job.res_stride + job.res_off + c0 : nullptr;
+#pragma unroll
+  for (int v = 0; v < 32 / V; ++v) {
+    float f[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      f[j] = __uint_as_float(r[v * V + j]);
+      if (relu) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (res) {
+      float e[V];
+      Act<T>::load(res + v * V, e);
+#pragma unroll
+      for (int j = 0; j < V; ++j) f[j] += e[j];
+    }
+    Act<T>::store(out + v * V, f);
+  }
+}
+
+template <int NACC>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcKParams p) {
+  using Cfg = TcCfg<NACC>;
+  constexpr int NPB = Cfg::kPatchStages;
+  constexpr int TILE_H = NACC * kTcRowsPerAcc;
+  constexpr uint32_t ROW_BYTES = kTcTileW * 128;   // one image row of a patch
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_patch = sbase;
+  const uint32_t s_b = sbase + NPB * Cfg::kPatchBytes;
+  const uint32_t s_bar = s_b + kBStages * kBStageBytes;
+  // barrier map (8 B each)
+  const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * NPB;
+  const uint32_t bar_b_full = s_bar + 16 * NPB, bar_b_empty = bar_b_full + 8 * kBStages;
+  const uint32_t bar_acc_full = bar_b_empty + 8 * kBStages, bar_acc_empty = bar_acc_full + 16;
+  const uint32_t s_tmem_slot = bar_acc_empty + 16;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (s_tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    for (int i = 0; i < NPB; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem_slot), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================================ producer ================================================
+    if (lane == 0) {
+      int ps = 0, bs = 0;
+      uint32_t pph = 0, bph = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const Tile tl = decode_tile(p, t, TILE_H);
+        const TcJob& job = p.job[tl.job];
+        for (int s = 0; s < p.nslab; ++s) {
+          const uint8_t* wslab = job.w + (size_t)s * p.slab_bytes;
+          for (int dxi = 0; dxi < p.ndx; ++dxi) {
+            mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
+            mbar_expect_tx(bar_patch_full + 8 * ps, p.patch_tx);
+            tma_load_4d(s_patch + ps * Cfg::kPatchBytes, &tmap, bar_patch_full + 8 * ps,
+                        job.in_coff + s * p.slab_elems, tl.x0 + p.dx_ord[dxi] - p.pad, tl.y0 - p.pad, tl.n);
+            if (++ps == NPB) { ps = 0; pph ^= 1; }
+            for (int dyi = 0; dyi < p.ndy; ++dyi) {
+              mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
+              const uint32_t bytes = p.b_bytes[dxi][dyi];
+              mbar_expect_tx(bar_b_full + 8 * bs, bytes);
+              bulk_load(s_b + bs * kBStageBytes, wslab + p.b_off[dxi][dyi], bytes, bar_b_full + 8 * bs);
+              if (++bs == kBStages) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==============================================
+    if (lane == 0) {
+      int ps = 0, bs = 0;
+      uint32_t pph = 0, bph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const Tile tl = decode_tile(p, t, TILE_H);
+        const TcJob& job = p.job[tl.job];
+        const int buf = it % p.nbuf;
+        const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
+        mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * NACC * p.n_cols);
+        uint32_t first = 1;
+        for (int s = 0; s < p.nslab; ++s) {
+          for (int dxi = 0; dxi < p.ndx; ++dxi) {
+            mbar_wait(bar_patch_full + 8 * ps, pph);
+            tc_fence_after();
+            const uint32_t patch = s_patch + ps * Cfg::kPatchBytes;
+            for (int dyi = 0; dyi < p.ndy; ++dyi) {
+              mbar_wait(bar_b_full + 8 * bs, bph);
+              tc_fence_after();
+              const bool half = p.b_bytes[dxi][dyi] < (uint32_t)p.n_cols * 128u;
+              const uint32_t idesc = half ? p.idesc_half : p.idesc_full;
+              const uint32_t col = half ? (uint32_t)job.outer_col : 0u;
+              const uint64_t bdesc = umma_desc(s_b + bs * kBStageBytes);
+#pragma unroll
+              for (int j = 0; j < NACC; ++j) {
+                const uint64_t adesc = umma_desc(patch + (uint32_t)(j * kTcRowsPerAcc + p.dy_ord[dyi]) * ROW_BYTES);
+                const uint32_t d = d_base + (uint32_t)(j * p.n_cols) + col;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t acc = (first && k == 0) ? 0u : 1u;
+                  // +32 B per K step inside the 128-B swizzled row == +2 in the 16-B address field
+                  if (p.is_tf32) umma_tf32(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                  else           umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                }
+              }
+              first = 0;
+              umma_commit(bar_b_empty + 8 * bs);
+              if (++bs == kBStages) { bs = 0; bph ^= 1; }
+            }
+            umma_commit(bar_patch_empty + 8 * ps);
+            if (++ps == NPB) { ps = 0; pph ^= 1; }
+          }
+        }
+        umma_commit(bar_acc_full + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue =================================================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;                 // accumulator row == pixel inside the sub-tile
+    const int my = m / kTcTileW, mx = m % kTcTileW;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const Tile tl = decode_tile(p, t, TILE_H);
+      const TcJob& job = p.job[tl.job];
+      const int buf = it % p.nbuf;
+      const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
+      mbar_wait(bar_acc_full + 8 * buf, aph);
+      tc_fence_after();
+      const int px = tl.x0 + mx;
+#pragma unroll 1
+      for (int j = 0; j < NACC; ++j) {
+        const int py = tl.y0 + j * kTcRowsPerAcc + my;
+        const bool valid = (py < p.H) && (px < p.W);
+        const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
+        const uint32_t tcol = (uint32_t)(buf * NACC * p.n_cols + j * p.n_cols);
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.n_cols; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (valid) {
+            if (p.out_act == ACT_F32) store_chunk<float>(r, job, pix, c0, p.relu != 0);
+            else if (p.out_act == ACT_BF16) store_chunk<__nv_bfloat16>(r, job, pix, c0, p.relu != 0);
+            else store_chunk<__half>(r, job, pix, c0, p.relu != 0);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty + 8 * buf);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+
+uint32_t make_idesc(int operand, int n) {
+  // UMMA instruction descriptor: D = F32 (bits 4-5 = 1), A/B format (bits 7-9 / 10-12), both K-major,
+  // N >> 3 at bit 17, M >> 4 at bit 24 (M = 128).
+  return (1u << 4) | ((uint32_t)operand << 7) | ((uint32_t)operand << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+
+inline uint16_t f32_to_bf16(float f) {
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline uint16_t f32_to_f16(float f) {
+  __half h = __float2half_rn(f);
+  uint16_t r; memcpy(&r, &h, 2);
+  return r;
+}
+inline uint32_t f32_to_tf32(float f) {
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return u;
+  u += 0xfffu + ((u >> 13) & 1u);   // round to nearest even at bit 13
+  return u & ~0x1fffu;
+}
+
+// Writes element (row, k) of a K-major block with 128-B rows into its SWIZZLE_128B position.
+inline void put_elem(uint8_t* block, int row, int k, int esize, float v, int operand) {
+  const int byte_in_row = k * esize;
+  const int chunk = byte_in_row >> 4, within = byte_in_row & 15;
+  uint8_t* dst = block + (size_t)row * 128 + (size_t)((chunk ^ (row & 7)) << 4) + within;
+  if (operand == TC_TF32) { const uint32_t u = f32_to_tf32(v); memcpy(dst, &u, 4); }
+  else { const uint16_t u = operand == TC_BF16 ? f32_to_bf16(v) : f32_to_f16(v); memcpy(dst, &u, 2); }
+}
+
+void fill_orders(TcConvPlan& p, bool centre_first) {
+  p.ndx = p.ndy = p.ks;
+  if (centre_first && p.ks == 5) {
+    const int ord[5] = {2, 1, 3, 0, 4};
+    for (int i = 0; i < 5; ++i) p.dx_ord[i] = p.dy_ord[i] = ord[i];
+  } else {
+    for (int i = 0; i < p.ks; ++i) p.dx_ord[i] = p.dy_ord[i] = i;
+  }
+}
+
+}  // namespace
+
+TcConvPlan tc_make_plan(int ks, int cin, int cout, int operand) {
+  TcConvPlan p;
+  p.ks = ks; p.operand = operand;
+  const int esize = operand == TC_TF32 ? 4 : 2;
+  p.slab_elems = 128 / esize;
+  p.nslab = cin / p.slab_elems;
+  p.n_cols = cout;
+  p.pair = 0;
+  fill_orders(p, false);
+  uint32_t off = 0;
+  for (int dxi = 0; dxi < p.ndx; ++dxi)
+    for (int dyi = 0; dyi < p.ndy; ++dyi) {
+      p.b_bytes[dxi][dyi] = (uint32_t)cout * 128u;
+      p.b_off[dxi][dyi] = off;
+      off += p.b_bytes[dxi][dyi];
+    }
+  p.slab_bytes = off;
+  return p;
+}
+
+TcConvPlan tc_make_pair_plan(int cin, int operand) {
+  TcConvPlan p;
+  p.ks = 5; p.operand = operand;
+  const int esize = operand == TC_TF32 ? 4 : 2;
+  p.slab_elems = 128 / esize;
+  p.nslab = cin / p.slab_elems;
+  p.n_cols = 128;
+  p.pair = 1;
+  fill_orders(p, true);   // the first tap issued must cover all 128 columns (accumulate = 0)
+  uint32_t off = 0;
+  for (int dxi = 0; dxi < 5; ++dxi)
+    for (int dyi = 0; dyi < 5; ++dyi) {
+      const bool inner = std::abs(p.dx_ord[dxi] - 2) <= 1 && std::abs(p.dy_ord[dyi] - 2) <= 1;
+      p.b_bytes[dxi][dyi] = (inner ? 128u : 64u) * 128u;
+      p.b_off[dxi][dyi] = off;
+      off += p.b_bytes[dxi][dyi];
+    }
+  p.slab_bytes = off;
+  return p;
+}
+
+void tc_pack_weights(const TcConvPlan& p, const float* w, std::vector<uint8_t>& dst) {
+  const int esize = p.operand == TC_TF32 ? 4 : 2;
+  const int cin = p.nslab * p.slab_elems, ks = p.ks, cout = p.n_cols;
+  dst.assign(p.total_bytes(), 0);
+  for (int s = 0; s < p.nslab; ++s)
+    for (int dxi = 0; dxi < p.ndx; ++dxi)
+      for (int dyi = 0; dyi < p.ndy; ++dyi) {
+        uint8_t* block = dst.data() + (size_t)s * p.slab_bytes + p.b_off[dxi][dyi];
+        const int dx = p.dx_ord[dxi], dy = p.dy_ord[dyi];
+        for (int n = 0; n < cout; ++n)
+          for (int k = 0; k < p.slab_elems; ++k) {
+            const int ci = s * p.slab_elems + k;
+            put_elem(block, n, k, esize, w[(((size_t)n * cin + ci) * ks + dy) * ks + dx], p.operand);
+          }
+      }
+}
+
+void tc_pack_pair_weights(const TcConvPlan& p, const float* w3, const float* w5, bool three_first,
+                          std::vector<uint8_t>& dst) {
+  const int esize = p.operand == TC_TF32 ? 4 : 2;
+  const int cin = p.nslab * p.slab_elems;
+  dst.assign(p.total_bytes(), 0);
+  const int row3 = three_first ? 0 : 64, row5 = three_first ? 64 : 0;
+  for (int s = 0; s < p.nslab; ++s)
+    for (int dxi = 0; dxi < 5; ++dxi)
+      for (int dyi = 0; dyi < 5; ++dyi) {
+        uint8_t* block = dst.data() + (size_t)s * p.slab_bytes + p.b_off[dxi][dyi];
+        const int dx = p.dx_ord[dxi], dy = p.dy_ord[dyi];
+        const bool inner = p.b_bytes[dxi][dyi] == 128u * 128u;
+        for (int n = 0; n < 64; ++n)
+          for (int k = 0; k < p.slab_elems; ++k) {
+            const int ci = s * p.slab_elems + k;
+            const float v5 = w5[(((size_t)n * cin + ci) * 5 + dy) * 5 + dx];
+            put_elem(block, inner ? row5 + n : n, k, esize, v5, p.operand);
+            if (inner) {
+              const float v3 = w3[(((size_t)n * cin + ci) * 3 + (dy - 1)) * 3 + (dx - 1)];
+              put_elem(block, row3 + n, k, esize, v3, p.operand);
+            }
+          }
+      }
+}
+
+cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, int W, int H, int B,
+                           int slab_elems, int box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const int es = act_bytes(act);
+  const CUtensorMapDataType dt = act == ACT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                               : act == ACT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+  const cuuint32_t box[4] = {(cuuint32_t)slab_elems, (cuuint32_t)kTcTileW, (cuuint32_t)box_rows, 1u};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode(map, dt, 4, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+namespace {
+template <int NACC>
+cudaError_t launch_nacc(const CUtensorMap& tmap, TcKParams& kp, cudaStream_t st) {
+  using Cfg = TcCfg<NACC>;
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const int tile_h = NACC * kTcRowsPerAcc;
+  kp.tiles_y = cdiv(kp.H, tile_h);
+  kp.tiles_per_job = kp.B * kp.tiles_x * kp.tiles_y;
+  kp.total_tiles = kp.tiles_per_job * kp.njobs;
+  kp.nbuf = (2 * NACC * kp.n_cols <= 512) ? 2 : 1;
+  kp.patch_tx = (uint32_t)(tile_h + kp.ks - 1) * kTcTileW * 128u;
+  const int grid = kp.total_tiles < num_sms ? kp.total_tiles : num_sms;
+  conv_tc_kernel<NACC><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmap, kp);
+  return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t launch_conv_tc(const CUtensorMap& tmap, const TcConvPlan& plan, const TcLaunch& L, cudaStream_t st) {
+  TcKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  for (int i = 0; i < L.njobs; ++i) kp.job[i] = L.job[i];
+  kp.njobs = L.njobs; kp.B = L.B; kp.H = L.H; kp.W = L.W;
+  kp.tiles_x = cdiv(L.W, kTcTileW);
+  kp.nslab = plan.nslab; kp.slab_elems = plan.slab_elems; kp.ks = plan.ks; kp.pad = plan.ks / 2;
+  kp.ndx = plan.ndx; kp.ndy = plan.ndy;
+  for (int i = 0; i < kTcMaxTaps; ++i) { kp.dx_ord[i] = plan.dx_ord[i]; kp.dy_ord[i] = plan.dy_ord[i]; }
+  memcpy(kp.b_bytes, plan.b_bytes, sizeof(kp.b_bytes));
+  memcpy(kp.b_off, plan.b_off, sizeof(kp.b_off));
+  kp.slab_bytes = plan.slab_bytes;
+  kp.n_cols = plan.n_cols;
+  kp.idesc_full = make_idesc(plan.operand, plan.n_cols);
+  kp.idesc_half = make_idesc(plan.operand, 64);
+  kp.relu = L.relu; kp.out_act = L.out_act; kp.is_tf32 = plan.operand == TC_TF32;
+  switch (L.nacc) {
+    case 1: return launch_nacc<1>(tmap, kp, st);
+    case 2: return launch_nacc<2>(tmap, kp, st);
+    case 4: return launch_nacc<4>(tmap, kp, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace codon

@@ -1,0 +1,75 @@
+// tcgen05 implicit-GEMM convolution: host-visible plan / launch structures (see conv_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+
+namespace codon {
+
+constexpr int kTcTileW = 16;          // tile width in pixels: one patch row = 16 px * 128 B = 2 KB
+constexpr int kTcRowsPerAcc = 8;      // 128 / kTcTileW image rows per 128-row accumulator
+constexpr int kTcMaxTaps = 5;
+
+enum TcOperand : int { TC_F16 = 0, TC_BF16 = 1, TC_TF32 = 2 };   // == UMMA F16F32Format
+
+// Geometry of the packed B (weight) stream of one convolution: for every 128-byte input-channel
+// slab, for every tap in issue order, one K-major block of `rows` x 128 B, already in the
+// SWIZZLE_128B shared-memory image, so the kernel fetches it with one cp.async.bulk.
+struct TcConvPlan {
+  int ks = 1;                  // 1, 3, 5
+  int nslab = 1;               // Cin * elem_bytes / 128
+  int slab_elems = 64;         // 64 (16-bit operands) or 32 (tf32)
+  int n_cols = 64;             // accumulator columns per pixel (Cout of the fused layer(s))
+  int pair = 0;                // 1: fused 3x3 + 5x5 pair (inner taps 128 rows, outer taps 64)
+  int ndx = 1, ndy = 1;
+  int dx_ord[kTcMaxTaps] = {0, 0, 0, 0, 0};
+  int dy_ord[kTcMaxTaps] = {0, 0, 0, 0, 0};
+  uint32_t b_bytes[kTcMaxTaps][kTcMaxTaps] = {};   // [dxi][dyi]
+  uint32_t b_off[kTcMaxTaps][kTcMaxTaps] = {};     // byte offset inside one slab group
+  uint32_t slab_bytes = 0;
+  int operand = TC_BF16;
+  size_t total_bytes() const { return (size_t)slab_bytes * nslab; }
+};
+
+// Plans.  `cout`/`cin` in elements; the pair plan is 64 -> (64 | 64) with kernel sizes 3 and 5.
+TcConvPlan tc_make_plan(int ks, int cin, int cout, int operand);
+TcConvPlan tc_make_pair_plan(int cin, int operand);
+
+// Pack OIHW fp32 weights into the plan's byte stream.  For a pair plan, w3 (3x3) and w5 (5x5)
+// are both [64][cin][k][k]; `three_first` puts the 3x3 result in columns 0..63 (depth branch,
+// CODON_x4.py:79) and the 5x5 result in 64..127, otherwise the other way round (colour branch
+// :80 and fusion stages :125).  `in_perm` (may be null) maps packed input channel -> OIHW input
+// channel.
+void tc_pack_weights(const TcConvPlan& plan, const float* w, std::vector<uint8_t>& dst);
+void tc_pack_pair_weights(const TcConvPlan& plan, const float* w3, const float* w5, bool three_first,
+                          std::vector<uint8_t>& dst);
+
+struct TcJob {
+  int in_coff;                 // channel coordinate of the job's first input channel in the tensor map
+  const uint8_t* w;            // device pointer to the packed stream
+  void* out;       int out_stride; int out_off;   // elements
+  const void* res; int res_stride; int res_off;
+  int outer_col;               // pair plans: accumulator column of the 5x5-only (outer) taps
+};
+
+struct TcLaunch {
+  TcJob job[2];
+  int njobs = 1;
+  int B = 0, H = 0, W = 0;
+  int relu = 0;
+  int out_act = 0;             // ActType of out / res
+  int nacc = 4;                // accumulators (128-pixel sub-tiles) per CTA tile: 1, 2 or 4
+};
+
+// Box height (image rows) the A tensor map must be encoded with for this plan / nacc.
+inline int tc_box_rows(const TcConvPlan& p, int nacc) { return nacc * kTcRowsPerAcc + p.ks - 1; }
+
+// Encodes the 4-D NHWC tensor map {C, W, H, B} with box {slab_elems, 16, box_rows, 1}, SWIZZLE_128B.
+cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, int W, int H, int B,
+                           int slab_elems, int box_rows);
+
+cudaError_t launch_conv_tc(const CUtensorMap& tmap, const TcConvPlan& plan, const TcLaunch& L,
+                           cudaStream_t st);
+
+}  // namespace codon

@@ -1,0 +1,73 @@
+// Host-side launchers of the hand-written kernels (internal to libcodon_b200).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace codon {
+
+// One convolution "job" of a launch.  A launch runs up to two jobs (the depth and the colour
+// branch of a stage) over the same B x H x W pixel grid.  Tensors are NHWC with an arbitrary
+// pixel stride (channels of the whole buffer) and a channel offset, so producers write into
+// channel slices of a shared buffer and torch.cat (CODON_x4.py:79,80,85,119,125) disappears.
+struct ConvJob {
+  const void* in;  int in_stride;  int in_off;    // elements
+  const void* w;                                   // layout depends on the kernel
+  void* out;       int out_stride; int out_off;
+  const void* res; int res_stride; int res_off;   // optional residual added after (no) ReLU
+};
+
+// ---- fp32 CUDA-core direct convolution (parity mode) -------------------------------------
+// w: fp32 [KS*KS][Cin][Cout].  Cin % 8 == 0, Cout % 64 == 0.
+cudaError_t launch_conv_direct_f32(const ConvJob* jobs, int njobs, int B, int H, int W,
+                                   int Cin, int Cout, int KS, bool relu, cudaStream_t st);
+
+// ---- edge layers (all modes) ----------------------------------------------------------------
+// input / input_c: 1 -> 64, 3x3, ReLU (CODON_x4.py:68,71).  x, y fp32 [B,H,W]; w_d, w_c fp32
+// [9][64]; out NHWC 128 ch (depth | colour) of type act.
+cudaError_t launch_conv_first(const float* x, const float* y, const float* w_d, const float* w_c,
+                              void* out, int act, int B, int H, int W, cudaStream_t st);
+// output: 64 -> 1, 3x3, + global residual x (CODON_x4.py:130-131).  in NHWC 64 ch of type act
+// (pixel stride in_stride); w fp32 [9][64]; x, out fp32 [B,H,W].
+cudaError_t launch_conv_last(const void* in, int in_stride, int act, const float* w, const float* x,
+                             float* out, int B, int H, int W, cudaStream_t st);
+
+// ---- CAC cross-domain attention (CAC_module.py, CODON_x4.py:85-118) -------------------------
+// F: NHWC 128 ch (depth | colour).  stats: per-pixel (max, mean) over the 128 channels ->
+// pooled [B,H,W,2] fp32, and per-chunk partial per-channel (sum, max) -> part [B][chunks][2][128].
+int cac_stats_chunks(int B, int H, int W);
+cudaError_t launch_cac_stats(const void* F, int act, int B, int H, int W, float* pooled,
+                             float* part, int chunks, cudaStream_t st);
+// mlp: deterministic reduce of the partials, MLP 128->8->64 on avg and max, sigmoid -> sc [B,64].
+// w1 [8][128] indexed by Fcat channel (colour | depth, CODON_x4.py:85), b1 [8], w2 [64][8], b2 [64].
+cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const float* w1,
+                           const float* b1, const float* w2, const float* b2, float* sc,
+                           cudaStream_t st);
+// apply: F = F * sc[b, c % 64] * sigmoid(conv5x5(pooled))[b,h,w] + E   (in place on F).
+// ws fp32 [2][25] (max map taps, then mean map taps).
+cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* pooled, const float* sc,
+                             const float* ws, int B, int H, int W, cudaStream_t st);
+
+// ---- utility -------------------------------------------------------------------------------------
+cudaError_t launch_convert_to_f32(const void* src, int dtype, float* dst, size_t n, cudaStream_t st);
+cudaError_t launch_convert_from_f32(const float* src, void* dst, int dtype, size_t n, cudaStream_t st);
+// NHWC (type act, pixel stride `stride`, channel offset `off`, C channels) -> fp32 NCHW
+cudaError_t launch_nhwc_to_nchw_f32(const void* src, int act, int stride, int off, int C, int B, int HW,
+                                    float* dst, cudaStream_t st);
+
+// ---- stand-alone NCHW fp32 CAC / CBAM pieces ----------------------------------------------------
+cudaError_t launch_nchw_channel_stats(const float* x, int B, int C, int HW, float* avg, float* mx,
+                                      cudaStream_t st);
+cudaError_t launch_gate_mlp(const float* avg, const float* mx, int B, int C, const float* w1,
+                            const float* b1, const float* w2, const float* b2, int hidden, int c_out,
+                            float* scale, cudaStream_t st);
+cudaError_t launch_nchw_channel_pool(const float* x, int B, int C, int HW, float* pooled, cudaStream_t st);
+cudaError_t launch_nchw_spatial_scale(const float* pooled, const float* w, int B, int H, int W,
+                                      float* scale, cudaStream_t st);
+cudaError_t launch_nchw_apply(const float* x, const float* sc, const float* ss, const float* res, int B,
+                              int C, int HW, int c_gate, float* y, cudaStream_t st);
+
+// ---- tcgen05 implicit-GEMM convolution (BF16 / FP16 / TF32 modes), conv_tc.cu -------------------
+struct TcConvPlan;   // defined in conv_tc.h
+
+}  // namespace codon

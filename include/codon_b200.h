@@ -1,0 +1,133 @@
+/*
+ * codon_b200.h -- C ABI of libcodon_b200.so: the B200 (sm_100a) engine for the CODON guided
+ * depth super-resolution forward pass.
+ *
+ * The reference (619862306/CODON) is pure Python/PyTorch and has no native interface to
+ * mirror; each entry point below names the reference call it replaces (paths relative to the
+ * reference checkout).  Plain pointers and sizes only: no torch types cross this boundary.
+ * The Python host (codon_b200/engine.py) binds these with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns CODON_OK (0) or a negative codon_status; the message of the
+ *     last failure on a context is available from codon_last_error().
+ *   - device pointers are borrowed for the duration of the stream-ordered call; the library
+ *     owns only its re-laid-out weight copies.
+ *   - frames are single-channel, row-major, B x H x W (== NCHW == NHWC for C = 1), values in
+ *     normalised depth / gray [0,1] as produced by CODON_X4/test.py:122-123.
+ *   - there is no CPU fallback: without a CUDA device every call fails with CODON_ERR_CUDA.
+ */
+#ifndef CODON_B200_H
+#define CODON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct codon_ctx codon_ctx;
+
+typedef enum codon_status {
+  CODON_OK = 0,
+  CODON_ERR_ARG = -1,       /* bad argument (null pointer, unknown name, wrong shape) */
+  CODON_ERR_STATE = -2,     /* call order (e.g. forward before finalize_weights) */
+  CODON_ERR_CUDA = -3,      /* CUDA runtime / driver failure, or no device */
+  CODON_ERR_WORKSPACE = -4  /* workspace too small */
+} codon_status;
+
+/* Arithmetic mode of the conv trunk.
+ *   FP32 : fp32 activations, fp32 FFMA direct convolution (parity mode, max-abs <= 1e-3).
+ *   BF16 : bf16 NHWC activations, tcgen05 kind::f16 (bf16 operands), fp32 accumulation in TMEM.
+ *   FP16 : as BF16 with fp16 operands (what the reference runs on GPU: model.half(),
+ *          CODON_X4/test.py:52).
+ *   TF32 : fp32 NHWC activations, tcgen05 kind::tf32, fp32 accumulation.
+ * In every mode the depth input, the global residual add and the output stay fp32, and the
+ * CAC statistics / gates are computed in fp32. */
+typedef enum codon_mode {
+  CODON_MODE_FP32 = 0,
+  CODON_MODE_BF16 = 1,
+  CODON_MODE_FP16 = 2,
+  CODON_MODE_TF32 = 3
+} codon_mode;
+
+/* dtype of the frames passed to codon_forward */
+typedef enum codon_dtype {
+  CODON_DTYPE_F32 = 0,
+  CODON_DTYPE_F16 = 1,
+  CODON_DTYPE_BF16 = 2
+} codon_dtype;
+
+/* Replaces: CODONNet() + .cuda().half() + .eval()  (CODON_X4/test.py:48,52,67;
+ * CODON_X16/test.py:51-55).  scale is 4, 8 or 16 and only selects the expected parameter
+ * set (x4/x8 carry the unused attention_c5/attention_s5 keys, CODON_X4/CODON_x4.py:64-65). */
+int codon_create(codon_ctx** out, int device, int scale, int mode);
+void codon_destroy(codon_ctx* ctx);
+const char* codon_last_error(const codon_ctx* ctx);   /* ctx may be NULL: last global error */
+const char* codon_version(void);
+
+/* Replaces: model.load_state_dict(...)  (CODON_X4/test.py:59, CODON_X16/test.py:60).
+ * name is the reference state_dict key ("conv3.weight", "attention_c0.mlp.1.bias", ...; a
+ * leading "module." from DataParallel is accepted); data is HOST fp32 in the PyTorch layout
+ * (OIHW for convolutions, [out,in] for Linear).  Keys of the never-executed
+ * attention_c5 / attention_s5 are accepted and ignored.  codon_finalize_weights re-lays the
+ * weights out for the kernels (tap-major, pre-swizzled K-major slabs) and uploads them; it
+ * fails if a parameter the forward needs is missing. */
+int codon_set_weight(codon_ctx* ctx, const char* name, const float* data,
+                     const int64_t* shape, int ndim);
+int codon_finalize_weights(codon_ctx* ctx);
+
+/* Bytes of device scratch codon_forward needs for B frames of H x W (activations live here
+ * so that the memory stays owned by and visible to the caller's allocator). */
+size_t codon_workspace_bytes(const codon_ctx* ctx, int B, int H, int W);
+
+/* Replaces: out = model(input_pic, gray_pic)  (CODON_X4/test.py:125, CODON_X16/test.py:132;
+ * CODONNet.forward, CODON_X4/CODON_x4.py:66-132).  depth, guide, out: DEVICE pointers to
+ * B*H*W elements of io_dtype.  Asynchronous on cuda_stream (a cudaStream_t, may be NULL for
+ * the legacy default stream).  A context is not re-entrant: one in-flight forward per
+ * ctx/workspace. */
+int codon_forward(codon_ctx* ctx, const void* depth, const void* guide, void* out,
+                  int B, int H, int W, int io_dtype,
+                  void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* End-to-end variant with HOST frames (what test.py does around the model call,
+ * CODON_X4/test.py:122-128): copies depth/guide from host, runs the forward, copies the
+ * result back and synchronises.  Frames are fp32.  The context keeps pinned staging buffers
+ * and its own workspace for this entry point. */
+int codon_forward_host(codon_ctx* ctx, const float* depth, const float* guide, float* out,
+                       int B, int H, int W);
+
+/* Number of kernels the last codon_forward on this context launched. */
+int codon_last_launch_count(const codon_ctx* ctx);
+
+/* Copies an intermediate activation of the last forward to dst as fp32 NCHW [B,C,H,W]
+ * (DEVICE pointer, C returned through channels).  Names: "enc" (128: depth|colour encoder
+ * outputs), "feat" (128: depth|colour stage outputs after the last stage), "ms" (256),
+ * "fuse" (64), "out_fuse" (64).  For layer-level parity tests. */
+int codon_debug_tap(codon_ctx* ctx, const char* name, float* dst, int* channels,
+                    void* cuda_stream);
+
+/* ---- stand-alone CAC / CBAM pieces (unit-testable; NCHW fp32 DEVICE tensors) -------------
+ * Replaces CAC_channel.forward (CODON_X4/CAC_module.py:38-63): x [B,C,H,W] -> scale [B,C_out]
+ * (the reference returns it expanded to [B,C_out,H,W]); w1 [hidden,C], b1 [hidden],
+ * w2 [C_out,hidden], b2 [C_out] are DEVICE fp32.  Also serves attention/ResCBAM.py:38-61
+ * (ChannelGate) with C_out == C. */
+int codon_cac_channel(const float* x, int B, int C, int H, int W,
+                      const float* w1, const float* b1, const float* w2, const float* b2,
+                      int hidden, int c_out, float* scale, void* cuda_stream);
+/* Replaces CAC_spatial.forward (CODON_X4/CAC_module.py:90-94) and ChannelPool (:78-81):
+ * x [B,C,H,W] -> scale [B,1,H,W]; w [1,2,5,5] DEVICE fp32 (channel 0 weights the max map,
+ * channel 1 the mean map).  pooled (may be NULL) receives the [B,2,H,W] ChannelPool output. */
+int codon_cac_spatial(const float* x, int B, int C, int H, int W, const float* w,
+                      float* scale, float* pooled, void* cuda_stream);
+/* Gate + residual (CODON_X4/CODON_x4.py:88-91,117-118): y = x * sc[b,c % c_gate] * ss[b,h,w]
+ * (+ res if res != NULL); sc may be NULL (ones) and ss may be NULL (ones), which gives
+ * ChannelGate / SpatialGate (attention/ResCBAM.py:61,87). */
+int codon_cac_apply(const float* x, const float* sc, const float* ss, const float* res,
+                    int B, int C, int H, int W, int c_gate, float* y, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CODON_B200_H */
