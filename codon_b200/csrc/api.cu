@@ -1,0 +1,691 @@
+// libcodon_b200: C ABI (include/codon_b200.h) and the forward-pass launch plan.
+//
+// The plan is the B200 restatement of CODONNet.forward (CODON_X4/CODON_x4.py:66-132 ==
+// CODON_X8/CODON_x8.py; CODON_X16/CODON_x16.py:136-202).  Activations are NHWC in a caller
+// provided workspace; the torch.cat calls of the reference (:79,80,85,119,125) are replaced by
+// producers writing into channel slices of shared buffers:
+//
+//   E    128 ch  [enc_d | enc_c]      encoder outputs = residual carriers of the 5 stages (:70,73)
+//   F    128 ch  [out_d | out_c]      stage outputs; conv7 reads it as cat(out, out_c) (:119)
+//   MS   256 ch  [ms_d | ms_c]        multi-scale pairs: depth [3x3|5x5] (:79), colour [5x5|3x3] (:80)
+//   R2   256 ch  [r2_d | r2_c]        conv3 / conv6 outputs (:81-82)
+//   FUSE  64 ch  conv7 output = residual carrier of the fusion stages (:120-121)
+//   OF    64 ch  out_fuse (:127-128)
+//
+// One launch handles the depth and the colour branch of a layer as two "jobs".
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/codon_b200.h"
+#include "common.cuh"
+#include "conv_tc.h"
+#include "kernels.h"
+
+using namespace codon;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+struct ConvSpec { const char* name; int cout, cin, ks; };
+// CODON_X4/CODON_x4.py:24-47
+const ConvSpec kTrunk[] = {
+    {"input", 64, 1, 3},    {"conv_input", 64, 64, 3}, {"conv1", 64, 64, 3},   {"conv2", 64, 64, 5},
+    {"conv3", 128, 128, 5}, {"confuse", 64, 128, 1},   {"input_c", 64, 1, 3},  {"conv_input_c", 64, 64, 3},
+    {"conv4", 64, 64, 5},   {"conv5", 64, 64, 3},      {"conv6", 128, 128, 5}, {"confuse_c", 64, 128, 1},
+    {"conv7", 64, 128, 3},  {"conv8", 64, 64, 5},      {"conv9", 64, 64, 3},   {"conv10", 128, 128, 5},
+    {"confuse_fuse", 64, 128, 1}, {"conv11", 64, 64, 3}, {"output", 1, 64, 3}};
+
+struct TcLayer {
+  TcConvPlan plan;
+  uint8_t* dev = nullptr;
+};
+
+struct Buffers {
+  // byte offsets into the workspace
+  size_t xf = 0, yf = 0, of32 = 0, E = 0, F = 0, MS = 0, R2 = 0, FUSE = 0, OF = 0, pooled = 0, part = 0, sc = 0;
+  size_t total = 0;
+  int chunks = 0;
+};
+
+}  // namespace
+
+struct codon_ctx {
+  int device = 0, scale = 4, mode = 0, act = ACT_F32;
+  bool finalized = false;
+  std::map<std::string, HostTensor> host_w;
+  std::string err;
+  int launches = 0;
+  std::vector<void*> dev_allocs;
+
+  // fp32 direct-conv weights [T][Cin][Cout]
+  std::map<std::string, float*> w_direct;
+  // tcgen05 packed weights
+  std::map<std::string, TcLayer> w_tc;
+  float *w_in_d = nullptr, *w_in_c = nullptr, *w_out = nullptr;   // [9][64]
+  float *cac_w1[5] = {}, *cac_b1[5] = {}, *cac_w2[5] = {}, *cac_b2[5] = {}, *cac_ws[5] = {};
+
+  // tensor-map cache (valid while workspace / shape unchanged)
+  struct MapKey {
+    const void* base; int C, box_rows, B, H, W;
+    bool operator<(const MapKey& o) const {
+      return std::tie(base, C, box_rows, B, H, W) < std::tie(o.base, o.C, o.box_rows, o.B, o.H, o.W);
+    }
+  };
+  std::map<MapKey, CUtensorMap> tmaps;
+
+  // last forward (debug taps)
+  uint8_t* last_ws = nullptr;
+  Buffers last_buf;
+  int last_B = 0, last_H = 0, last_W = 0;
+
+  // codon_forward_host state
+  cudaStream_t host_stream = nullptr;
+  void* host_ws = nullptr; size_t host_ws_bytes = 0;
+  float *pin_in = nullptr, *pin_out = nullptr; size_t pin_elems = 0;
+  float *dev_x = nullptr, *dev_y = nullptr, *dev_o = nullptr; size_t dev_elems = 0;
+};
+
+namespace {
+
+int fail(codon_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(ctx, CODON_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W) {
+  Buffers b;
+  const size_t P = (size_t)B * H * W, e = act_bytes(ctx->act);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  b.xf = take(P * 4); b.yf = take(P * 4); b.of32 = take(P * 4);
+  b.E = take(P * 128 * e); b.F = take(P * 128 * e);
+  b.MS = take(P * 256 * e); b.R2 = take(P * 256 * e);
+  b.FUSE = take(P * 64 * e); b.OF = take(P * 64 * e);
+  b.pooled = take(P * 2 * 4);
+  b.chunks = cac_stats_chunks(B, H, W);
+  b.part = take((size_t)B * b.chunks * 256 * 4);
+  b.sc = take((size_t)B * 64 * 4);
+  b.total = off + 1024;   // slack for aligning the caller's pointer
+  return b;
+}
+
+template <typename T>
+int upload(codon_ctx* ctx, const std::vector<T>& host, T** dev) {
+  void* p = nullptr;
+  CU_TRY(ctx, cudaMalloc(&p, host.size() * sizeof(T)));
+  ctx->dev_allocs.push_back(p);
+  CU_TRY(ctx, cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dev = static_cast<T*>(p);
+  return CODON_OK;
+}
+
+const HostTensor* find_w(const codon_ctx* ctx, const std::string& key) {
+  auto it = ctx->host_w.find(key);
+  return it == ctx->host_w.end() ? nullptr : &it->second;
+}
+
+// OIHW -> [T][Cin][Cout]
+std::vector<float> to_tap_major(const HostTensor& t, int cout, int cin, int ks) {
+  std::vector<float> r((size_t)ks * ks * cin * cout);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int k = 0; k < ks * ks; ++k)
+        r[((size_t)k * cin + ci) * cout + co] = t.data[((size_t)co * cin + ci) * ks * ks + k];
+  return r;
+}
+
+int get_tmap(codon_ctx* ctx, const void* base, int C, int box_rows, int slab_elems, int B, int H, int W,
+             const CUtensorMap** out) {
+  codon_ctx::MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.C = C; key.box_rows = box_rows; key.B = B; key.H = H; key.W = W;
+  auto it = ctx->tmaps.find(key);
+  if (it == ctx->tmaps.end()) {
+    if (ctx->tmaps.size() > 256) ctx->tmaps.clear();
+    CUtensorMap m;
+    CU_TRY(ctx, tc_encode_tmap(&m, base, ctx->act, C, W, H, B, slab_elems, box_rows));
+    it = ctx->tmaps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return CODON_OK;
+}
+
+int pick_nacc(int B, int H, int W, int njobs) {
+  const int tx = cdiv(W, kTcTileW);
+  for (int nacc : {4, 2}) {
+    const long tiles = (long)B * tx * cdiv(H, nacc * kTcRowsPerAcc) * njobs;
+    if (tiles >= 2 * 148) return nacc;
+  }
+  return 1;
+}
+
+// One conv layer of the plan: up to two jobs reading channel slices of `in` (in_C channels).
+struct LayerJob { const char* w; int in_off; size_t out; int out_stride, out_off; size_t res; int res_stride, res_off; bool has_res; };
+
+struct Runner {
+  codon_ctx* ctx; uint8_t* ws; int B, H, W; cudaStream_t st; int e;
+
+  int conv(const char* plan_name, size_t in, int in_C, int cin, int cout, int ks, bool relu,
+           const LayerJob* jobs, int njobs) {
+    if (ctx->mode == CODON_MODE_FP32) {
+      ConvJob cj[2];
+      for (int i = 0; i < njobs; ++i) {
+        cj[i].in = ws + in; cj[i].in_stride = in_C; cj[i].in_off = jobs[i].in_off;
+        cj[i].w = ctx->w_direct.at(jobs[i].w);
+        cj[i].out = ws + jobs[i].out; cj[i].out_stride = jobs[i].out_stride; cj[i].out_off = jobs[i].out_off;
+        cj[i].res = jobs[i].has_res ? ws + jobs[i].res : nullptr;
+        cj[i].res_stride = jobs[i].res_stride; cj[i].res_off = jobs[i].res_off;
+      }
+      CU_TRY(ctx, launch_conv_direct_f32(cj, njobs, B, H, W, cin, cout, ks, relu, st));
+      ctx->launches++;
+      return CODON_OK;
+    }
+    (void)plan_name;
+    const TcLayer& l0 = ctx->w_tc.at(jobs[0].w);
+    TcLaunch L;
+    L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = relu; L.out_act = ctx->act;
+    L.nacc = pick_nacc(B, H, W, njobs);
+    for (int i = 0; i < njobs; ++i) {
+      const TcLayer& l = ctx->w_tc.at(jobs[i].w);
+      L.job[i].in_coff = jobs[i].in_off;
+      L.job[i].w = l.dev;
+      L.job[i].out = ws + jobs[i].out; L.job[i].out_stride = jobs[i].out_stride; L.job[i].out_off = jobs[i].out_off;
+      L.job[i].res = jobs[i].has_res ? ws + jobs[i].res : nullptr;
+      L.job[i].res_stride = jobs[i].res_stride; L.job[i].res_off = jobs[i].res_off;
+      L.job[i].outer_col = 0;
+    }
+    const CUtensorMap* tm = nullptr;
+    int rc = get_tmap(ctx, ws + in, in_C, tc_box_rows(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
+    if (rc) return rc;
+    CU_TRY(ctx, launch_conv_tc(*tm, l0.plan, L, st));
+    ctx->launches++;
+    return CODON_OK;
+  }
+
+  // 3x3 || 5x5 multi-scale pair on a 64-channel input slice -> 128 output channels at out_off.
+  // three_first[i]: job i writes [3x3 | 5x5] (depth branch) else [5x5 | 3x3].
+  int pair(size_t in, int in_C, const int* in_off, const char* const* w3, const char* const* w5,
+           const char* const* wpair, const bool* three_first, size_t out, int out_stride, const int* out_off,
+           int njobs) {
+    if (ctx->mode == CODON_MODE_FP32) {
+      LayerJob j3[2], j5[2];
+      for (int i = 0; i < njobs; ++i) {
+        j3[i] = {w3[i], in_off[i], out, out_stride, out_off[i] + (three_first[i] ? 0 : 64), 0, 0, 0, false};
+        j5[i] = {w5[i], in_off[i], out, out_stride, out_off[i] + (three_first[i] ? 64 : 0), 0, 0, 0, false};
+      }
+      int rc = conv("", in, in_C, 64, 64, 3, true, j3, njobs);
+      if (rc) return rc;
+      return conv("", in, in_C, 64, 64, 5, true, j5, njobs);
+    }
+    const TcLayer& l0 = ctx->w_tc.at(wpair[0]);
+    TcLaunch L;
+    L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = 1; L.out_act = ctx->act;
+    L.nacc = pick_nacc(B, H, W, njobs);
+    for (int i = 0; i < njobs; ++i) {
+      const TcLayer& l = ctx->w_tc.at(wpair[i]);
+      L.job[i].in_coff = in_off[i];
+      L.job[i].w = l.dev;
+      L.job[i].out = ws + out; L.job[i].out_stride = out_stride; L.job[i].out_off = out_off[i];
+      L.job[i].res = nullptr; L.job[i].res_stride = 0; L.job[i].res_off = 0;
+      L.job[i].outer_col = three_first[i] ? 64 : 0;
+    }
+    const CUtensorMap* tm = nullptr;
+    int rc = get_tmap(ctx, ws + in, in_C, tc_box_rows(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
+    if (rc) return rc;
+    CU_TRY(ctx, launch_conv_tc(*tm, l0.plan, L, st));
+    ctx->launches++;
+    return CODON_OK;
+  }
+};
+
+int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int B, int H, int W, uint8_t* ws,
+                const Buffers& bf, cudaStream_t st) {
+  Runner r{ctx, ws, B, H, W, st, act_bytes(ctx->act)};
+  int rc;
+  // encoders (CODON_x4.py:68-73): input/input_c 1->64 (+ReLU) into the R2 region viewed as 128 ch
+  const size_t T0 = bf.R2;
+  CU_TRY(ctx, launch_conv_first(x, y, ctx->w_in_d, ctx->w_in_c, ws + T0, ctx->act, B, H, W, st));
+  ctx->launches++;
+  {
+    LayerJob j[2] = {{"conv_input", 0, bf.E, 128, 0, 0, 0, 0, false}, {"conv_input_c", 64, bf.E, 128, 64, 0, 0, 0, false}};
+    if ((rc = r.conv("", T0, 128, 64, 64, 3, true, j, 2))) return rc;
+  }
+  // five multi-scale + CAC stages (:74-118)
+  for (int s = 0; s < 5; ++s) {
+    const size_t src = s == 0 ? bf.E : bf.F;
+    {
+      const int in_off[2] = {0, 64}, out_off[2] = {0, 128};
+      const char* w3[2] = {"conv1", "conv5"}; const char* w5[2] = {"conv2", "conv4"};
+      const char* wp[2] = {"pair_d", "pair_c"};
+      const bool tf[2] = {true, false};
+      if ((rc = r.pair(src, 128, in_off, w3, w5, wp, tf, bf.MS, 256, out_off, 2))) return rc;
+    }
+    {
+      LayerJob j[2] = {{"conv3", 0, bf.R2, 256, 0, 0, 0, 0, false}, {"conv6", 128, bf.R2, 256, 128, 0, 0, 0, false}};
+      if ((rc = r.conv("", bf.MS, 256, 128, 128, 5, true, j, 2))) return rc;
+    }
+    {
+      LayerJob j[2] = {{"confuse", 0, bf.F, 128, 0, 0, 0, 0, false}, {"confuse_c", 128, bf.F, 128, 64, 0, 0, 0, false}};
+      if ((rc = r.conv("", bf.R2, 256, 128, 64, 1, false, j, 2))) return rc;
+    }
+    // CAC gates (:85-118, CAC_module.py:38-63, 78-94)
+    float* pooled = reinterpret_cast<float*>(ws + bf.pooled);
+    float* part = reinterpret_cast<float*>(ws + bf.part);
+    float* sc = reinterpret_cast<float*>(ws + bf.sc);
+    CU_TRY(ctx, launch_cac_stats(ws + bf.F, ctx->act, B, H, W, pooled, part, bf.chunks, st));
+    CU_TRY(ctx, launch_cac_mlp(part, bf.chunks, B, H * W, ctx->cac_w1[s], ctx->cac_b1[s], ctx->cac_w2[s],
+                               ctx->cac_b2[s], sc, st));
+    CU_TRY(ctx, launch_cac_apply(ws + bf.F, ws + bf.E, ctx->act, pooled, sc, ctx->cac_ws[s], B, H, W, st));
+    ctx->launches += 3;
+  }
+  // fusion head (:119-121): cat(out, out_c) is F itself
+  {
+    LayerJob j[1] = {{"conv7", 0, bf.FUSE, 64, 0, 0, 0, 0, false}};
+    if ((rc = r.conv("", bf.F, 128, 128, 64, 3, true, j, 1))) return rc;
+  }
+  // three fusion stages (:122-128)
+  for (int k = 0; k < 3; ++k) {
+    const size_t src = k == 0 ? bf.FUSE : bf.OF;
+    {
+      const int in_off[1] = {0}, out_off[1] = {0};
+      const char* w3[1] = {"conv9"}; const char* w5[1] = {"conv8"}; const char* wp[1] = {"pair_f"};
+      const bool tf[1] = {false};
+      if ((rc = r.pair(src, 64, in_off, w3, w5, wp, tf, bf.MS, 256, out_off, 1))) return rc;
+    }
+    {
+      LayerJob j[1] = {{"conv10", 0, bf.R2, 256, 0, 0, 0, 0, false}};
+      if ((rc = r.conv("", bf.MS, 256, 128, 128, 5, true, j, 1))) return rc;
+    }
+    {
+      LayerJob j[1] = {{"confuse_fuse", 0, bf.OF, 64, 0, bf.FUSE, 64, 0, true}};
+      if ((rc = r.conv("", bf.R2, 256, 128, 64, 1, false, j, 1))) return rc;
+    }
+  }
+  // reconstruction (:129-131): conv11 into the MS region viewed as 64 ch, then output + x
+  {
+    LayerJob j[1] = {{"conv11", 0, bf.MS, 64, 0, 0, 0, 0, false}};
+    if ((rc = r.conv("", bf.OF, 64, 64, 64, 3, true, j, 1))) return rc;
+  }
+  CU_TRY(ctx, launch_conv_last(ws + bf.MS, 64, ctx->act, ctx->w_out, x, out, B, H, W, st));
+  ctx->launches++;
+  return CODON_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* codon_version(void) { return "codon_b200 0.1 (sm_100a)"; }
+
+const char* codon_last_error(const codon_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int codon_create(codon_ctx** out, int device, int scale, int mode) {
+  if (!out) return fail(nullptr, CODON_ERR_ARG, "codon_create: out is NULL");
+  *out = nullptr;
+  if (scale != 4 && scale != 8 && scale != 16) return fail(nullptr, CODON_ERR_ARG, "codon_create: scale must be 4, 8 or 16 (got %d)", scale);
+  if (mode < CODON_MODE_FP32 || mode > CODON_MODE_TF32) return fail(nullptr, CODON_ERR_ARG, "codon_create: unknown mode %d", mode);
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, CODON_ERR_CUDA, "codon_create: no CUDA device (%s); there is no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= n) return fail(nullptr, CODON_ERR_ARG, "codon_create: device %d out of range [0,%d)", device, n);
+  cudaDeviceProp prop;
+  CU_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, CODON_ERR_CUDA, "codon_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  CU_TRY(nullptr, cudaSetDevice(device));
+  codon_ctx* c = new codon_ctx();
+  c->device = device; c->scale = scale; c->mode = mode;
+  c->act = mode == CODON_MODE_BF16 ? ACT_BF16 : mode == CODON_MODE_FP16 ? ACT_F16 : ACT_F32;
+  *out = c;
+  return CODON_OK;
+}
+
+void codon_destroy(codon_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (void* p : ctx->dev_allocs) cudaFree(p);
+  if (ctx->host_ws) cudaFree(ctx->host_ws);
+  if (ctx->dev_x) cudaFree(ctx->dev_x);
+  if (ctx->dev_y) cudaFree(ctx->dev_y);
+  if (ctx->dev_o) cudaFree(ctx->dev_o);
+  if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
+  if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+  if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
+  delete ctx;
+}
+
+int codon_set_weight(codon_ctx* ctx, const char* name, const float* data, const int64_t* shape, int ndim) {
+  if (!ctx || !name || !data || !shape || ndim < 1 || ndim > 4) return fail(ctx, CODON_ERR_ARG, "codon_set_weight: bad argument");
+  std::string key(name);
+  if (key.rfind("module.", 0) == 0) key = key.substr(7);   // DataParallel prefix (CODON_X16/test.py:52,60)
+  // validate against the parameter inventory
+  std::vector<int64_t> shp(shape, shape + ndim), want;
+  const std::string base = key.substr(0, key.find('.'));
+  bool known = false;
+  for (const ConvSpec& s : kTrunk)
+    if (key == std::string(s.name) + ".weight") { want = {s.cout, s.cin, s.ks, s.ks}; known = true; }
+  if (!known && base.rfind("attention_c", 0) == 0 && base.size() == 12) {
+    const int k = base[11] - '0';
+    const int C = k == 5 ? 64 : 128, hid = k == 5 ? 4 : 8;
+    if (k >= 0 && k <= 5) {
+      const std::string rest = key.substr(base.size());
+      if (rest == ".mlp.1.weight") { want = {hid, C}; known = true; }
+      else if (rest == ".mlp.1.bias") { want = {hid}; known = true; }
+      else if (rest == ".mlp.3.weight") { want = {64, hid}; known = true; }
+      else if (rest == ".mlp.3.bias") { want = {64}; known = true; }
+    }
+  }
+  if (!known && base.rfind("attention_s", 0) == 0 && base.size() == 12 && base[11] >= '0' && base[11] <= '5' &&
+      key.substr(base.size()) == ".spatial.conv.weight") { want = {1, 2, 5, 5}; known = true; }
+  if (!known) return fail(ctx, CODON_ERR_ARG, "codon_set_weight: unexpected key '%s'", name);
+  if (shp != want) return fail(ctx, CODON_ERR_ARG, "codon_set_weight: shape mismatch for '%s'", name);
+  size_t n = 1;
+  for (int64_t d : shp) n *= (size_t)d;
+  HostTensor t;
+  t.shape = shp;
+  t.data.assign(data, data + n);
+  ctx->host_w[key] = std::move(t);
+  ctx->finalized = false;
+  return CODON_OK;
+}
+
+int codon_finalize_weights(codon_ctx* ctx) {
+  if (!ctx) return fail(nullptr, CODON_ERR_ARG, "codon_finalize_weights: ctx is NULL");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (const ConvSpec& s : kTrunk)
+    if (!find_w(ctx, std::string(s.name) + ".weight"))
+      return fail(ctx, CODON_ERR_STATE, "codon_finalize_weights: missing parameter '%s.weight'", s.name);
+  for (int k = 0; k < 5; ++k)
+    for (const char* suf : {"c%d.mlp.1.weight", "c%d.mlp.1.bias", "c%d.mlp.3.weight", "c%d.mlp.3.bias", "s%d.spatial.conv.weight"}) {
+      char buf[64], key[96];
+      snprintf(buf, sizeof(buf), suf, k);
+      snprintf(key, sizeof(key), "attention_%s", buf);
+      if (!find_w(ctx, key)) return fail(ctx, CODON_ERR_STATE, "codon_finalize_weights: missing parameter '%s'", key);
+    }
+  // drop earlier uploads
+  for (void* p : ctx->dev_allocs) cudaFree(p);
+  ctx->dev_allocs.clear(); ctx->w_direct.clear(); ctx->w_tc.clear(); ctx->tmaps.clear();
+
+  int rc;
+  auto W = [&](const char* n) -> const HostTensor& { return *find_w(ctx, std::string(n) + ".weight"); };
+  // edge layers: [9][64]
+  {
+    std::vector<float> a(576), b(576), c(576);
+    for (int t = 0; t < 9; ++t)
+      for (int ch = 0; ch < 64; ++ch) {
+        a[t * 64 + ch] = W("input").data[ch * 9 + t];
+        b[t * 64 + ch] = W("input_c").data[ch * 9 + t];
+        c[t * 64 + ch] = W("output").data[ch * 9 + t];
+      }
+    if ((rc = upload(ctx, a, &ctx->w_in_d)) || (rc = upload(ctx, b, &ctx->w_in_c)) || (rc = upload(ctx, c, &ctx->w_out))) return rc;
+  }
+  for (int k = 0; k < 5; ++k) {
+    char key[96];
+    auto G = [&](const char* fmt) -> const std::vector<float>& { snprintf(key, sizeof(key), fmt, k); return find_w(ctx, key)->data; };
+    if ((rc = upload(ctx, G("attention_c%d.mlp.1.weight"), &ctx->cac_w1[k])) ||
+        (rc = upload(ctx, G("attention_c%d.mlp.1.bias"), &ctx->cac_b1[k])) ||
+        (rc = upload(ctx, G("attention_c%d.mlp.3.weight"), &ctx->cac_w2[k])) ||
+        (rc = upload(ctx, G("attention_c%d.mlp.3.bias"), &ctx->cac_b2[k])) ||
+        (rc = upload(ctx, G("attention_s%d.spatial.conv.weight"), &ctx->cac_ws[k]))) return rc;
+  }
+  if (ctx->mode == CODON_MODE_FP32) {
+    for (const ConvSpec& s : kTrunk) {
+      if (s.cin == 1 || s.cout == 1) continue;
+      float* d = nullptr;
+      if ((rc = upload(ctx, to_tap_major(W(s.name), s.cout, s.cin, s.ks), &d))) return rc;
+      ctx->w_direct[s.name] = d;
+    }
+  } else {
+    const int operand = ctx->mode == CODON_MODE_BF16 ? TC_BF16 : ctx->mode == CODON_MODE_FP16 ? TC_F16 : TC_TF32;
+    std::vector<uint8_t> packed;
+    for (const ConvSpec& s : kTrunk) {
+      if (s.cin == 1 || s.cout == 1) continue;
+      TcLayer l;
+      l.plan = tc_make_plan(s.ks, s.cin, s.cout, operand);
+      tc_pack_weights(l.plan, W(s.name).data.data(), packed);
+      if ((rc = upload(ctx, packed, &l.dev))) return rc;
+      ctx->w_tc[s.name] = l;
+    }
+    struct PairSpec { const char* name; const char* w3; const char* w5; bool three_first; };
+    // depth [3x3|5x5] (:75,77,79); colour [5x5|3x3] (:76,78,80); fusion [5x5|3x3] (:123-125)
+    for (const PairSpec& p : {PairSpec{"pair_d", "conv1", "conv2", true}, PairSpec{"pair_c", "conv5", "conv4", false},
+                              PairSpec{"pair_f", "conv9", "conv8", false}}) {
+      TcLayer l;
+      l.plan = tc_make_pair_plan(64, operand);
+      tc_pack_pair_weights(l.plan, W(p.w3).data.data(), W(p.w5).data.data(), p.three_first, packed);
+      if ((rc = upload(ctx, packed, &l.dev))) return rc;
+      ctx->w_tc[p.name] = l;
+    }
+  }
+  ctx->finalized = true;
+  return CODON_OK;
+}
+
+size_t codon_workspace_bytes(const codon_ctx* ctx, int B, int H, int W) {
+  if (!ctx || B < 1 || H < 1 || W < 1) return 0;
+  return plan_buffers(ctx, B, H, W).total;
+}
+
+int codon_forward(codon_ctx* ctx, const void* depth, const void* guide, void* out, int B, int H, int W,
+                  int io_dtype, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (!ctx) return fail(nullptr, CODON_ERR_ARG, "codon_forward: ctx is NULL");
+  if (!ctx->finalized) return fail(ctx, CODON_ERR_STATE, "codon_forward: weights not finalized");
+  if (!depth || !guide || !out || !workspace) return fail(ctx, CODON_ERR_ARG, "codon_forward: NULL pointer");
+  if (B < 1 || H < 1 || W < 1) return fail(ctx, CODON_ERR_ARG, "codon_forward: bad shape %dx%dx%d", B, H, W);
+  if ((size_t)B * H * W >= (1u << 30)) return fail(ctx, CODON_ERR_ARG, "codon_forward: more than 2^30 pixels per call");
+  if (io_dtype < CODON_DTYPE_F32 || io_dtype > CODON_DTYPE_BF16) return fail(ctx, CODON_ERR_ARG, "codon_forward: unknown io_dtype %d", io_dtype);
+  const Buffers bf = plan_buffers(ctx, B, H, W);
+  if (workspace_bytes < bf.total)
+    return fail(ctx, CODON_ERR_WORKSPACE, "codon_forward: workspace %zu B < required %zu B", workspace_bytes, bf.total);
+  for (const void* p : {depth, guide, (const void*)out, (const void*)workspace}) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+      cudaGetLastError();
+      return fail(ctx, CODON_ERR_ARG, "codon_forward: pointer %p is not device memory (no CPU path)", p);
+    }
+  }
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+  const size_t P = (size_t)B * H * W;
+  ctx->launches = 0;
+  const float *x = static_cast<const float*>(depth), *y = static_cast<const float*>(guide);
+  float* o = static_cast<float*>(out);
+  if (io_dtype != CODON_DTYPE_F32) {
+    float* xf = reinterpret_cast<float*>(ws + bf.xf);
+    float* yf = reinterpret_cast<float*>(ws + bf.yf);
+    CU_TRY(ctx, launch_convert_to_f32(depth, io_dtype, xf, P, st));
+    CU_TRY(ctx, launch_convert_to_f32(guide, io_dtype, yf, P, st));
+    ctx->launches += 2;
+    x = xf; y = yf; o = reinterpret_cast<float*>(ws + bf.of32);
+  }
+  int rc = run_forward(ctx, x, y, o, B, H, W, ws, bf, st);
+  if (rc) return rc;
+  if (io_dtype != CODON_DTYPE_F32) {
+    CU_TRY(ctx, launch_convert_from_f32(o, out, io_dtype, P, st));
+    ctx->launches++;
+  }
+  ctx->last_ws = ws; ctx->last_buf = bf; ctx->last_B = B; ctx->last_H = H; ctx->last_W = W;
+  return CODON_OK;
+}
+
+int codon_forward_host(codon_ctx* ctx, const float* depth, const float* guide, float* out, int B, int H, int W) {
+  if (!ctx) return fail(nullptr, CODON_ERR_ARG, "codon_forward_host: ctx is NULL");
+  if (!depth || !guide || !out) return fail(ctx, CODON_ERR_ARG, "codon_forward_host: NULL pointer");
+  if (B < 1 || H < 1 || W < 1) return fail(ctx, CODON_ERR_ARG, "codon_forward_host: bad shape");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t P = (size_t)B * H * W;
+  if (!ctx->host_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
+  if (ctx->pin_elems < P) {
+    if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
+    if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+    ctx->pin_in = ctx->pin_out = nullptr; ctx->pin_elems = 0;
+    CU_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->pin_in), 2 * P * sizeof(float)));
+    CU_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->pin_out), P * sizeof(float)));
+    ctx->pin_elems = P;
+  }
+  if (ctx->dev_elems < P) {
+    for (float** p : {&ctx->dev_x, &ctx->dev_y, &ctx->dev_o}) { if (*p) cudaFree(*p); *p = nullptr; }
+    ctx->dev_elems = 0;
+    CU_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->dev_x), P * sizeof(float)));
+    CU_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->dev_y), P * sizeof(float)));
+    CU_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->dev_o), P * sizeof(float)));
+    ctx->dev_elems = P;
+  }
+  const size_t need = codon_workspace_bytes(ctx, B, H, W);
+  if (ctx->host_ws_bytes < need) {
+    if (ctx->host_ws) cudaFree(ctx->host_ws);
+    ctx->host_ws = nullptr; ctx->host_ws_bytes = 0;
+    CU_TRY(ctx, cudaMalloc(&ctx->host_ws, need));
+    ctx->host_ws_bytes = need;
+  }
+  cudaStream_t st = ctx->host_stream;
+  memcpy(ctx->pin_in, depth, P * sizeof(float));
+  memcpy(ctx->pin_in + P, guide, P * sizeof(float));
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->dev_x, ctx->pin_in, P * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->dev_y, ctx->pin_in + P, P * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = codon_forward(ctx, ctx->dev_x, ctx->dev_y, ctx->dev_o, B, H, W, CODON_DTYPE_F32, ctx->host_ws,
+                         ctx->host_ws_bytes, st);
+  if (rc) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->pin_out, ctx->dev_o, P * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaStreamSynchronize(st));
+  memcpy(out, ctx->pin_out, P * sizeof(float));
+  return CODON_OK;
+}
+
+int codon_last_launch_count(const codon_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int codon_debug_tap(codon_ctx* ctx, const char* name, float* dst, int* channels, void* cuda_stream) {
+  if (!ctx || !name || !dst || !channels) return fail(ctx, CODON_ERR_ARG, "codon_debug_tap: bad argument");
+  if (!ctx->last_ws) return fail(ctx, CODON_ERR_STATE, "codon_debug_tap: no forward has run");
+  const Buffers& bf = ctx->last_buf;
+  size_t off; int C, stride;
+  const std::string n(name);
+  if (n == "enc") { off = bf.E; C = 128; stride = 128; }
+  else if (n == "feat") { off = bf.F; C = 128; stride = 128; }
+  else if (n == "ms") { off = bf.MS; C = 256; stride = 256; }
+  else if (n == "fuse") { off = bf.FUSE; C = 64; stride = 64; }
+  else if (n == "out_fuse") { off = bf.OF; C = 64; stride = 64; }
+  else return fail(ctx, CODON_ERR_ARG, "codon_debug_tap: unknown tap '%s'", name);
+  *channels = C;
+  CU_TRY(ctx, launch_nhwc_to_nchw_f32(ctx->last_ws + off, ctx->act, stride, 0, C, ctx->last_B,
+                                      ctx->last_H * ctx->last_W, dst, static_cast<cudaStream_t>(cuda_stream)));
+  return CODON_OK;
+}
+
+// ---- stand-alone pieces --------------------------------------------------------------------------
+int codon_cac_channel(const float* x, int B, int C, int H, int W, const float* w1, const float* b1,
+                      const float* w2, const float* b2, int hidden, int c_out, int pool_mask, float* scale,
+                      void* cuda_stream) {
+  if (!x || !w1 || !b1 || !w2 || !b2 || !scale || B < 1 || C < 1 || H < 1 || W < 1 || hidden < 1 || c_out < 1 ||
+      pool_mask < 1 || pool_mask > 15)
+    return fail(nullptr, CODON_ERR_ARG, "codon_cac_channel: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  float* tmp = nullptr;
+  CU_TRY(nullptr, cudaMallocAsync(reinterpret_cast<void**>(&tmp), (size_t)4 * B * C * sizeof(float), st));
+  CU_TRY(nullptr, launch_nchw_channel_stats(x, B, C, H * W, pool_mask, tmp, st));
+  CU_TRY(nullptr, launch_gate_mlp(tmp, B, C, pool_mask, w1, b1, w2, b2, hidden, c_out, scale, st));
+  CU_TRY(nullptr, cudaFreeAsync(tmp, st));
+  return CODON_OK;
+}
+
+int codon_cac_spatial(const float* x, int B, int C, int H, int W, const float* w, float* scale, float* pooled,
+                      void* cuda_stream) {
+  if (!x || !w || !scale || B < 1 || C < 1 || H < 1 || W < 1) return fail(nullptr, CODON_ERR_ARG, "codon_cac_spatial: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  float* tmp = pooled;
+  if (!tmp) CU_TRY(nullptr, cudaMallocAsync(reinterpret_cast<void**>(&tmp), (size_t)2 * B * H * W * sizeof(float), st));
+  CU_TRY(nullptr, launch_nchw_channel_pool(x, B, C, H * W, tmp, st));
+  CU_TRY(nullptr, launch_nchw_spatial_scale(tmp, w, B, H, W, scale, st));
+  if (!pooled) CU_TRY(nullptr, cudaFreeAsync(tmp, st));
+  return CODON_OK;
+}
+
+int codon_cac_apply(const float* x, const float* sc, const float* ss, const float* res, int B, int C, int H, int W,
+                    int c_gate, float* y, void* cuda_stream) {
+  if (!x || !y || B < 1 || C < 1 || H < 1 || W < 1 || (sc && c_gate < 1)) return fail(nullptr, CODON_ERR_ARG, "codon_cac_apply: bad argument");
+  CU_TRY(nullptr, launch_nchw_apply(x, sc, ss, res, B, C, H * W, c_gate > 0 ? c_gate : 1, y, static_cast<cudaStream_t>(cuda_stream)));
+  return CODON_OK;
+}
+
+int codon_channel_stats(const float* x, int B, int C, int H, int W, float* stats, void* cuda_stream) {
+  if (!x || !stats || B < 1 || C < 1 || H < 1 || W < 1) return fail(nullptr, CODON_ERR_ARG, "codon_channel_stats: bad argument");
+  CU_TRY(nullptr, launch_nchw_channel_stats(x, B, C, H * W, 15, stats, static_cast<cudaStream_t>(cuda_stream)));
+  return CODON_OK;
+}
+
+int codon_channel_pool(const float* x, int B, int C, int H, int W, float* pooled, void* cuda_stream) {
+  if (!x || !pooled || B < 1 || C < 1 || H < 1 || W < 1) return fail(nullptr, CODON_ERR_ARG, "codon_channel_pool: bad argument");
+  CU_TRY(nullptr, launch_nchw_channel_pool(x, B, C, H * W, pooled, static_cast<cudaStream_t>(cuda_stream)));
+  return CODON_OK;
+}
+
+int codon_conv2d_nchw(const float* x, const float* w, const float* bias, int B, int Cin, int H, int W, int Cout,
+                      int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                      int groups, int relu, float* y, void* cuda_stream) {
+  if (!x || !w || !y || B < 1 || Cin < 1 || H < 1 || W < 1 || Cout < 1 || kh < 1 || kw < 1 || stride_h < 1 ||
+      stride_w < 1 || pad_h < 0 || pad_w < 0 || dil_h < 1 || dil_w < 1 || groups < 1 || Cin % groups || Cout % groups)
+    return fail(nullptr, CODON_ERR_ARG, "codon_conv2d_nchw: bad argument");
+  CU_TRY(nullptr, launch_conv2d_nchw(x, w, bias, B, Cin, H, W, Cout, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h,
+                                     dil_w, groups, relu, y, static_cast<cudaStream_t>(cuda_stream)));
+  return CODON_OK;
+}
+
+int codon_quantise_u8(const float* src, uint8_t* dst, size_t n, int via_half, void* cuda_stream) {
+  if (!src || !dst) return fail(nullptr, CODON_ERR_ARG, "codon_quantise_u8: NULL pointer");
+  if (n == 0) return CODON_OK;
+  CU_TRY(nullptr, launch_quantise_u8(src, dst, n, via_half, static_cast<cudaStream_t>(cuda_stream)));
+  return CODON_OK;
+}
+
+int codon_masked_rmse(const uint8_t* label, const uint8_t* out, int B, int H, int W, double* rmse, void* cuda_stream) {
+  if (!label || !out || !rmse || B < 1 || H < 1 || W < 1) return fail(nullptr, CODON_ERR_ARG, "codon_masked_rmse: bad argument");
+  CU_TRY(nullptr, launch_masked_rmse(label, out, B, H * W, rmse, static_cast<cudaStream_t>(cuda_stream)));
+  return CODON_OK;
+}
+
+int codon_ssim_gauss(const void* img1, const void* img2, int img_dtype, int B, int H, int W, double sd, double c1,
+                     double c2, double* ssim, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (!img1 || !img2 || !ssim || !workspace || B < 1 || H < 1 || W < 1 || !(sd > 0) || img_dtype < 0 || img_dtype > 1)
+    return fail(nullptr, CODON_ERR_ARG, "codon_ssim_gauss: bad argument");
+  if (workspace_bytes < ssim_workspace_bytes(B, H, W))
+    return fail(nullptr, CODON_ERR_WORKSPACE, "codon_ssim_gauss: workspace %zu B < required %zu B", workspace_bytes,
+                ssim_workspace_bytes(B, H, W));
+  CU_TRY(nullptr, launch_ssim_gauss(img1, img2, img_dtype, B, H, W, sd, c1, c2, ssim, static_cast<double*>(workspace),
+                                    static_cast<cudaStream_t>(cuda_stream)));
+  return CODON_OK;
+}
+
+}  // extern "C"

@@ -56,16 +56,28 @@ cudaError_t launch_nhwc_to_nchw_f32(const void* src, int act, int stride, int of
                                     float* dst, cudaStream_t st);
 
 // ---- stand-alone NCHW fp32 CAC / CBAM pieces ----------------------------------------------------
-cudaError_t launch_nchw_channel_stats(const float* x, int B, int C, int HW, float* avg, float* mx,
+// stats [4][B*C]: mean, max, lp(2), lse per (b,c) plane; pool_mask bit k selects pool k in the MLP sum
+cudaError_t launch_nchw_channel_stats(const float* x, int B, int C, int HW, int pool_mask, float* stats,
                                       cudaStream_t st);
-cudaError_t launch_gate_mlp(const float* avg, const float* mx, int B, int C, const float* w1,
-                            const float* b1, const float* w2, const float* b2, int hidden, int c_out,
-                            float* scale, cudaStream_t st);
+cudaError_t launch_gate_mlp(const float* stats, int B, int C, int pool_mask, const float* w1, const float* b1,
+                            const float* w2, const float* b2, int hidden, int c_out, float* scale,
+                            cudaStream_t st);
 cudaError_t launch_nchw_channel_pool(const float* x, int B, int C, int HW, float* pooled, cudaStream_t st);
 cudaError_t launch_nchw_spatial_scale(const float* pooled, const float* w, int B, int H, int W,
                                       float* scale, cudaStream_t st);
 cudaError_t launch_nchw_apply(const float* x, const float* sc, const float* ss, const float* res, int B,
                               int C, int HW, int c_gate, float* y, cudaStream_t st);
+
+cudaError_t launch_conv2d_nchw(const float* x, const float* w, const float* bias, int B, int Cin, int H, int W,
+                               int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int groups,
+                               int relu, float* y, cudaStream_t st);
+
+// ---- driver post-processing and metrics (metrics.cu) ---------------------------------------------
+cudaError_t launch_quantise_u8(const float* src, uint8_t* dst, size_t n, int via_half, cudaStream_t st);
+cudaError_t launch_masked_rmse(const uint8_t* label, const uint8_t* out, int B, int HW, double* rmse, cudaStream_t st);
+size_t ssim_workspace_bytes(int B, int H, int W);
+cudaError_t launch_ssim_gauss(const void* a, const void* b, int img_dtype, int B, int H, int W, double sd, double c1, double c2,
+                              double* ssim, double* ws, cudaStream_t st);
 
 // ---- tcgen05 implicit-GEMM convolution (BF16 / FP16 / TF32 modes), conv_tc.cu -------------------
 struct TcConvPlan;   // defined in conv_tc.h

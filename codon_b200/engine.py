@@ -1,0 +1,367 @@
+"""ctypes binding of libcodon_b200.so (include/codon_b200.h) and the Engine wrapper.
+
+PyTorch is plumbing here: it owns device memory (inputs, outputs, workspace) and streams; every
+arithmetic operation of the forward runs in the hand-written sm_100a kernels behind the C ABI.
+There is NO CPU path and NO fallback: if the library is missing or no CUDA device is present,
+calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Dict, Optional
+
+import torch
+
+from . import build as _build
+
+MODES = {"fp32": 0, "bf16": 1, "fp16": 2, "tf32": 3}
+_IO_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+# every symbol include/codon_b200.h declares (tests/test_abi.py checks the list against the header)
+ABI_SYMBOLS = [
+    "codon_create", "codon_destroy", "codon_last_error", "codon_version", "codon_set_weight",
+    "codon_finalize_weights", "codon_workspace_bytes", "codon_forward", "codon_forward_host",
+    "codon_last_launch_count", "codon_debug_tap", "codon_cac_channel", "codon_cac_spatial",
+    "codon_cac_apply", "codon_channel_stats", "codon_channel_pool", "codon_conv2d_nchw",
+    "codon_masked_rmse", "codon_ssim_gauss", "codon_quantise_u8",
+]
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class CodonError(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """Loads (once) the in-tree shared library and declares the argument types."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or _build.LIB_PATH
+        if not os.path.exists(p):
+            raise CodonError(
+                f"{p} not found: build it with `python -m codon_b200.build` (or __graft_entry__.build()). "
+                "codon_b200 has no CPU or PyTorch fallback.")
+        lib = ctypes.CDLL(p)
+        c = ctypes
+        vp, ip, fp = c.c_void_p, c.c_int, c.POINTER(c.c_float)
+        lib.codon_create.argtypes = [c.POINTER(vp), ip, ip, ip]
+        lib.codon_destroy.argtypes = [vp]
+        lib.codon_destroy.restype = None
+        lib.codon_last_error.argtypes = [vp]
+        lib.codon_last_error.restype = c.c_char_p
+        lib.codon_version.argtypes = []
+        lib.codon_version.restype = c.c_char_p
+        lib.codon_set_weight.argtypes = [vp, c.c_char_p, fp, c.POINTER(c.c_int64), ip]
+        lib.codon_finalize_weights.argtypes = [vp]
+        lib.codon_workspace_bytes.argtypes = [vp, ip, ip, ip]
+        lib.codon_workspace_bytes.restype = c.c_size_t
+        lib.codon_forward.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, vp, c.c_size_t, vp]
+        lib.codon_forward_host.argtypes = [vp, vp, vp, vp, ip, ip, ip]
+        lib.codon_last_launch_count.argtypes = [vp]
+        lib.codon_debug_tap.argtypes = [vp, c.c_char_p, vp, c.POINTER(ip), vp]
+        lib.codon_cac_channel.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, vp, ip, ip, ip, vp, vp]
+        lib.codon_cac_spatial.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, vp]
+        lib.codon_cac_apply.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, ip, vp, vp]
+        lib.codon_channel_stats.argtypes = [vp, ip, ip, ip, ip, vp, vp]
+        lib.codon_channel_pool.argtypes = [vp, ip, ip, ip, ip, vp, vp]
+        lib.codon_conv2d_nchw.argtypes = [vp, vp, vp] + [ip] * 15 + [vp, vp]
+        lib.codon_masked_rmse.argtypes = [vp, vp, ip, ip, ip, vp, vp]
+        lib.codon_ssim_gauss.argtypes = [vp, vp, ip, ip, ip, ip, c.c_double, c.c_double, c.c_double, vp, vp, c.c_size_t, vp]
+        lib.codon_quantise_u8.argtypes = [vp, vp, c.c_size_t, ip, vp]
+        for name in ABI_SYMBOLS:
+            fn = getattr(lib, name)
+            if name not in ("codon_destroy", "codon_last_error", "codon_version", "codon_workspace_bytes"):
+                fn.restype = c.c_int
+        if path is None:
+            _lib = lib
+        return lib
+
+
+def check(rc: int, ctx=None) -> None:
+    if rc != 0:
+        lib = load_library()
+        msg = lib.codon_last_error(ctx).decode("utf-8", "replace") if ctx else lib.codon_last_error(None).decode()
+        raise CodonError(f"libcodon_b200 error {rc}: {msg}")
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise CodonError(f"{what} must be a CUDA tensor: codon_b200 has no CPU path (got device {t.device})")
+
+
+def current_stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Engine:
+    """One `codon_ctx`: the weights of one CODONNet on one GPU, in one arithmetic mode.
+
+    Replaces ``CODONNet().cuda().half()`` + ``load_state_dict`` + ``model(depth, gray)``
+    (CODON_X4/test.py:48-59,125).
+    """
+
+    def __init__(self, scale: int = 4, mode: str = "bf16", device: int | torch.device = 0):
+        if mode not in MODES:
+            raise ValueError(f"mode must be one of {sorted(MODES)}, got {mode!r}")
+        self.lib = load_library()
+        dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        if dev.type != "cuda":
+            raise CodonError("codon_b200.Engine needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.scale, self.mode = scale, mode
+        self._ctx = ctypes.c_void_p()
+        check(self.lib.codon_create(ctypes.byref(self._ctx), self.device.index, scale, MODES[mode]))
+        self._ws: Optional[torch.Tensor] = None
+        self._lock = threading.Lock()
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.codon_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights ---------------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """Accepts a reference state_dict (optionally with DataParallel's ``module.`` prefix)."""
+        for name, t in sd.items():
+            a = t.detach().to("cpu", torch.float32).contiguous()
+            shape = (ctypes.c_int64 * a.dim())(*a.shape)
+            check(self.lib.codon_set_weight(self._ctx, name.encode(), ctypes.cast(a.data_ptr(), ctypes.POINTER(ctypes.c_float)),
+                                            shape, a.dim()), self._ctx)
+        check(self.lib.codon_finalize_weights(self._ctx), self._ctx)
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def workspace_bytes(self, B: int, H: int, W: int) -> int:
+        return int(self.lib.codon_workspace_bytes(self._ctx, B, H, W))
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def forward(self, depth: torch.Tensor, guide: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """depth, guide: [B,1,H,W] (or [B,H,W]) CUDA tensors of one dtype (fp32 / fp16 / bf16);
+        returns [B,1,H,W] of that dtype.  Asynchronous on the current stream."""
+        _require_cuda(depth, "depth")
+        _require_cuda(guide, "guide")
+        if depth.shape != guide.shape or depth.dtype != guide.dtype:
+            raise CodonError(f"depth {tuple(depth.shape)}/{depth.dtype} and guide {tuple(guide.shape)}/{guide.dtype} differ")
+        if depth.dtype not in _IO_DTYPES:
+            raise CodonError(f"unsupported frame dtype {depth.dtype}")
+        if depth.dim() == 4:
+            if depth.shape[1] != 1:
+                raise CodonError(f"frames must be single-channel, got {tuple(depth.shape)}")
+            B, _, H, W = depth.shape
+        elif depth.dim() == 3:
+            B, H, W = depth.shape
+        else:
+            raise CodonError(f"frames must be [B,1,H,W] or [B,H,W], got {tuple(depth.shape)}")
+        depth, guide = depth.contiguous(), guide.contiguous()
+        if out is None:
+            out = torch.empty_like(depth)
+        with self._lock, torch.cuda.device(self.device):
+            ws = self._workspace(self.workspace_bytes(B, H, W))
+            check(self.lib.codon_forward(self._ctx, depth.data_ptr(), guide.data_ptr(), out.data_ptr(), B, H, W,
+                                         _IO_DTYPES[depth.dtype], ws.data_ptr(), ws.numel(),
+                                         current_stream_ptr(self.device)), self._ctx)
+        return out
+
+    __call__ = forward
+
+    def forward_host(self, depth, guide):
+        """HOST float32 numpy arrays [B,H,W] (or [B,1,H,W]) in, numpy out; copies included
+        (the reference's H2D / D2H around the model call, CODON_X4/test.py:122-128)."""
+        import numpy as np
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        g = np.ascontiguousarray(guide, dtype=np.float32)
+        if d.shape != g.shape:
+            raise CodonError("depth and guide shapes differ")
+        shp = d.shape
+        H, W = shp[-2], shp[-1]
+        B = int(d.size // (H * W))
+        out = np.empty_like(d)
+        with self._lock:
+            check(self.lib.codon_forward_host(self._ctx, d.ctypes.data, g.ctypes.data, out.ctypes.data, B, H, W), self._ctx)
+        return out
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.lib.codon_last_launch_count(self._ctx))
+
+    def debug_tap(self, name: str, B: int, H: int, W: int) -> torch.Tensor:
+        chans = {"enc": 128, "feat": 128, "ms": 256, "fuse": 64, "out_fuse": 64}[name]
+        dst = torch.empty(B, chans, H, W, dtype=torch.float32, device=self.device)
+        c = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.codon_debug_tap(self._ctx, name.encode(), dst.data_ptr(), ctypes.byref(c),
+                                           current_stream_ptr(self.device)), self._ctx)
+        return dst
+
+
+# ---- stand-alone attention pieces (module-level API of CAC_module / attention.ResCBAM) -------------
+
+POOL_BITS = {"avg": 1, "max": 2, "lp": 4, "lse": 8}
+
+
+def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    _require_cuda(t, what)
+    return t.detach().to(torch.float32).contiguous()
+
+
+def cac_channel_scale(x, w1, b1, w2, b2, pool_types=("avg", "max")) -> torch.Tensor:
+    """[B,C,H,W] -> [B,C_out] sigmoid gate (CAC_module.py:38-63 / ResCBAM.py:38-61)."""
+    lib = load_library()
+    xf = _f32c(x, "x")
+    B, C, H, W = xf.shape
+    w1f, b1f, w2f, b2f = (_f32c(t, "weight").to(xf.device) for t in (w1, b1, w2, b2))
+    hidden, c_out = w1f.shape[0], w2f.shape[0]
+    mask = 0
+    for p in pool_types:
+        mask |= POOL_BITS[p]
+    out = torch.empty(B, c_out, dtype=torch.float32, device=xf.device)
+    with torch.cuda.device(xf.device):
+        check(lib.codon_cac_channel(xf.data_ptr(), B, C, H, W, w1f.data_ptr(), b1f.data_ptr(), w2f.data_ptr(),
+                                    b2f.data_ptr(), hidden, c_out, mask, out.data_ptr(), current_stream_ptr(xf.device)))
+    return out
+
+
+def cac_spatial_scale(x, w, return_pooled: bool = False):
+    """[B,C,H,W] -> [B,1,H,W] sigmoid(conv5x5(ChannelPool(x))) (CAC_module.py:78-94)."""
+    lib = load_library()
+    xf = _f32c(x, "x")
+    B, C, H, W = xf.shape
+    wf = _f32c(w, "weight").to(xf.device)
+    out = torch.empty(B, 1, H, W, dtype=torch.float32, device=xf.device)
+    pooled = torch.empty(B, 2, H, W, dtype=torch.float32, device=xf.device)
+    with torch.cuda.device(xf.device):
+        check(lib.codon_cac_spatial(xf.data_ptr(), B, C, H, W, wf.data_ptr(), out.data_ptr(), pooled.data_ptr(),
+                                    current_stream_ptr(xf.device)))
+    return (out, pooled) if return_pooled else out
+
+
+def cac_apply(x, sc=None, ss=None, res=None) -> torch.Tensor:
+    """y = x * sc[b, c % c_gate] * ss[b,h,w] (+ res)   (CODON_x4.py:88-91,117-118; ResCBAM.py:61,87)."""
+    lib = load_library()
+    xf = _f32c(x, "x")
+    B, C, H, W = xf.shape
+    scf = _f32c(sc, "sc") if sc is not None else None
+    ssf = _f32c(ss, "ss") if ss is not None else None
+    rf = _f32c(res, "res") if res is not None else None
+    y = torch.empty_like(xf)
+    with torch.cuda.device(xf.device):
+        check(lib.codon_cac_apply(xf.data_ptr(), scf.data_ptr() if scf is not None else None,
+                                  ssf.data_ptr() if ssf is not None else None,
+                                  rf.data_ptr() if rf is not None else None, B, C, H, W,
+                                  scf.shape[1] if scf is not None else 1, y.data_ptr(), current_stream_ptr(xf.device)))
+    return y
+
+
+def channel_stats(x) -> torch.Tensor:
+    """[B,C,H,W] -> [4,B,C]: mean, max, lp(2), lse per plane (CAC_module.py:43,47,50-55,71-76)."""
+    lib = load_library()
+    xf = _f32c(x, "x")
+    B, C, H, W = xf.shape
+    out = torch.empty(4, B, C, dtype=torch.float32, device=xf.device)
+    with torch.cuda.device(xf.device):
+        check(lib.codon_channel_stats(xf.data_ptr(), B, C, H, W, out.data_ptr(), current_stream_ptr(xf.device)))
+    return out
+
+
+def channel_pool(x) -> torch.Tensor:
+    """ChannelPool (CAC_module.py:78-81): [B,C,H,W] -> [B,2,H,W] (max, mean)."""
+    lib = load_library()
+    xf = _f32c(x, "x")
+    B, C, H, W = xf.shape
+    out = torch.empty(B, 2, H, W, dtype=torch.float32, device=xf.device)
+    with torch.cuda.device(xf.device):
+        check(lib.codon_channel_pool(xf.data_ptr(), B, C, H, W, out.data_ptr(), current_stream_ptr(xf.device)))
+    return out
+
+
+def _pair(v):
+    return (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
+def conv2d_nchw(x, w, bias=None, stride=1, padding=0, dilation=1, groups=1, relu=False) -> torch.Tensor:
+    """Generic small NCHW fp32 convolution (BasicConv, CAC_module.py:6-20)."""
+    lib = load_library()
+    xf = _f32c(x, "x")
+    B, Cin, H, W = xf.shape
+    wf = _f32c(w, "weight").to(xf.device)
+    bf = _f32c(bias, "bias").to(xf.device) if bias is not None else None
+    Cout, _, kh, kw = wf.shape
+    (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
+    OH = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+    OW = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    y = torch.empty(B, Cout, OH, OW, dtype=torch.float32, device=xf.device)
+    with torch.cuda.device(xf.device):
+        check(lib.codon_conv2d_nchw(xf.data_ptr(), wf.data_ptr(), bf.data_ptr() if bf is not None else None,
+                                    B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, groups, int(relu),
+                                    y.data_ptr(), current_stream_ptr(xf.device)))
+    return y
+
+
+# ---- driver post-processing and metrics on the GPU -------------------------------------------------
+
+def quantise_u8(out: torch.Tensor, via_half: bool = False) -> torch.Tensor:
+    """clip(0,1) * 255 truncated to uint8 (CODON_X4/test.py:130,132)."""
+    lib = load_library()
+    of = _f32c(out, "out")
+    dst = torch.empty(of.shape, dtype=torch.uint8, device=of.device)
+    with torch.cuda.device(of.device):
+        check(lib.codon_quantise_u8(of.data_ptr(), dst.data_ptr(), of.numel(), int(via_half), current_stream_ptr(of.device)))
+    return dst
+
+
+def masked_rmse(label_u8: torch.Tensor, out_u8: torch.Tensor) -> torch.Tensor:
+    """EvaluationResults (CODON_X4/test.py:148-164) per frame: uint8 [B,H,W] CUDA tensors -> float64 [B]."""
+    lib = load_library()
+    _require_cuda(label_u8, "label")
+    _require_cuda(out_u8, "out")
+    o = out_u8.reshape(-1, out_u8.shape[-2], out_u8.shape[-1]).contiguous()
+    lab = label_u8.reshape(-1, label_u8.shape[-2], label_u8.shape[-1])[:, :o.shape[1], :o.shape[2]].contiguous()
+    if lab.dtype != torch.uint8 or o.dtype != torch.uint8 or lab.shape != o.shape:
+        raise CodonError("masked_rmse needs uint8 tensors of one shape")
+    B, H, W = o.shape
+    r = torch.empty(B, dtype=torch.float64, device=o.device)
+    with torch.cuda.device(o.device):
+        check(lib.codon_masked_rmse(lab.data_ptr(), o.data_ptr(), B, H, W, r.data_ptr(), current_stream_ptr(o.device)))
+    return r
+
+
+def ssim_gauss(img1: torch.Tensor, img2: torch.Tensor, sd: float = 1.5, c1: float = 0.01 ** 2,
+               c2: float = 0.03 ** 2) -> torch.Tensor:
+    """ssim_exact (CODON_X4/ssim_2.py:36-52) per frame.  uint8 inputs are scaled by 1/255 (the
+    driver's call, test.py:139); float inputs are used as float64 as given.  Returns float64 [B]."""
+    lib = load_library()
+    _require_cuda(img1, "img1")
+    _require_cuda(img2, "img2")
+    a = img1.reshape(-1, img1.shape[-2], img1.shape[-1])
+    b = img2.reshape(-1, img2.shape[-2], img2.shape[-1])
+    if a.shape != b.shape:
+        raise CodonError("ssim_gauss needs images of one shape")
+    if a.dtype == torch.uint8 and b.dtype == torch.uint8:
+        dt = 0
+        a, b = a.contiguous(), b.contiguous()
+    else:
+        dt = 1
+        a, b = a.to(torch.float64).contiguous(), b.to(torch.float64).contiguous()
+    B, H, W = a.shape
+    ws = torch.empty((5 * H * W + H) * B, dtype=torch.float64, device=a.device)
+    r = torch.empty(B, dtype=torch.float64, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.codon_ssim_gauss(a.data_ptr(), b.data_ptr(), dt, B, H, W, sd, c1, c2, r.data_ptr(), ws.data_ptr(),
+                                   ws.numel() * 8, current_stream_ptr(a.device)))
+    return r

@@ -111,11 +111,16 @@ int codon_debug_tap(codon_ctx* ctx, const char* name, float* dst, int* channels,
 /* ---- stand-alone CAC / CBAM pieces (unit-testable; NCHW fp32 DEVICE tensors) -------------
  * Replaces CAC_channel.forward (CODON_X4/CAC_module.py:38-63): x [B,C,H,W] -> scale [B,C_out]
  * (the reference returns it expanded to [B,C_out,H,W]); w1 [hidden,C], b1 [hidden],
- * w2 [C_out,hidden], b2 [C_out] are DEVICE fp32.  Also serves attention/ResCBAM.py:38-61
- * (ChannelGate) with C_out == C. */
+ * w2 [C_out,hidden], b2 [C_out] are DEVICE fp32.  pool_mask selects the pool_types summed into
+ * the gate (:40-61): bit 0 'avg', bit 1 'max', bit 2 'lp', bit 3 'lse'; the default
+ * ['avg','max'] is 3.  Also serves attention/ResCBAM.py:38-61 (ChannelGate) with C_out == C. */
+#define CODON_POOL_AVG 1
+#define CODON_POOL_MAX 2
+#define CODON_POOL_LP 4
+#define CODON_POOL_LSE 8
 int codon_cac_channel(const float* x, int B, int C, int H, int W,
                       const float* w1, const float* b1, const float* w2, const float* b2,
-                      int hidden, int c_out, float* scale, void* cuda_stream);
+                      int hidden, int c_out, int pool_mask, float* scale, void* cuda_stream);
 /* Replaces CAC_spatial.forward (CODON_X4/CAC_module.py:90-94) and ChannelPool (:78-81):
  * x [B,C,H,W] -> scale [B,1,H,W]; w [1,2,5,5] DEVICE fp32 (channel 0 weights the max map,
  * channel 1 the mean map).  pooled (may be NULL) receives the [B,2,H,W] ChannelPool output. */
@@ -126,6 +131,35 @@ int codon_cac_spatial(const float* x, int B, int C, int H, int W, const float* w
  * ChannelGate / SpatialGate (attention/ResCBAM.py:61,87). */
 int codon_cac_apply(const float* x, const float* sc, const float* ss, const float* res,
                     int B, int C, int H, int W, int c_gate, float* y, void* cuda_stream);
+
+/* Per-plane pooled statistics behind the pool_types of CAC_channel / ChannelGate
+ * (CAC_module.py:43,47,50-55,71-76): stats [4][B*C] DEVICE fp32 = mean, max, lp (p = 2), lse. */
+int codon_channel_stats(const float* x, int B, int C, int H, int W, float* stats, void* cuda_stream);
+/* ChannelPool (CAC_module.py:78-81): x [B,C,H,W] -> pooled [B,2,H,W] = (max over C, mean over C). */
+int codon_channel_pool(const float* x, int B, int C, int H, int W, float* pooled, void* cuda_stream);
+/* BasicConv (CAC_module.py:6-20): generic NCHW fp32 cross-correlation with optional bias (may be
+ * NULL) and ReLU; w [Cout, Cin/groups, kh, kw]; y [B, Cout, OH, OW] with the usual output size. */
+int codon_conv2d_nchw(const float* x, const float* w, const float* bias, int B, int Cin, int H, int W,
+                      int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w,
+                      int dil_h, int dil_w, int groups, int relu, float* y, void* cuda_stream);
+
+/* ---- driver post-processing and evaluation metrics on the GPU (DEVICE pointers) ---------------
+ * Replaces np.clip(out,0,1); (out*255).astype(np.uint8)  (CODON_X4/test.py:130,132): n fp32
+ * values -> uint8 by truncation.  via_half != 0 reproduces the reference's float16 evaluation
+ * (the model output there is a float16 array, test.py:52,127-128). */
+int codon_quantise_u8(const float* src, uint8_t* dst, size_t n, int via_half, void* cuda_stream);
+/* Replaces EvaluationResults (CODON_X4/test.py:148-164): label, out uint8 [B,H,W] (label already
+ * cropped to the output's size, :150); rmse[b] (DEVICE double) = RMSE in grey levels over the
+ * pixels with label != 0. */
+int codon_masked_rmse(const uint8_t* label, const uint8_t* out, int B, int H, int W, double* rmse,
+                      void* cuda_stream);
+/* Replaces ssim_exact(img1, img2, sd, C1, C2)  (CODON_X4/ssim_2.py:36-52): images [B,H,W] either
+ * uint8 (img_dtype 0; scaled by 1/255 as the driver does, test.py:139) or float64 (img_dtype 1,
+ * used as given); float64 arithmetic, scipy gaussian_filter semantics; ssim[b] DEVICE double.
+ * workspace: DEVICE scratch of at least (5*H*W + H) * B * 8 bytes. */
+int codon_ssim_gauss(const void* img1, const void* img2, int img_dtype, int B, int H, int W, double sd,
+                     double c1, double c2, double* ssim, void* workspace, size_t workspace_bytes,
+                     void* cuda_stream);
 
 #ifdef __cplusplus
 }

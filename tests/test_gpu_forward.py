@@ -1,0 +1,161 @@
+"""GPU parity: the CUDA forward (through the C ABI, via the CODONNet drop-in) against the committed
+reference outputs (tests/golden/fwd_*.npz, produced by the real reference) and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import codon_oracle as orc
+from codon_b200 import engine
+from codon_b200 import CODON_x4, CODON_x8, CODON_x16
+
+pytestmark = pytest.mark.gpu
+
+MODS = {4: CODON_x4, 8: CODON_x8, 16: CODON_x16}
+FWD = ["fwd_x4_s0_b2_48x64.npz", "fwd_x4_s1_b1_37x53.npz", "fwd_x8_s2_b1_40x72.npz", "fwd_x16_s2_b1_64x80.npz",
+       "fwd_x4_s0_b1_120x160.npz"]
+# max-abs tolerance in normalised depth vs the reference's fp64 forward.  north_star: fp32 mode <= 1e-3.
+# fp16 / tf32 operands (10-bit mantissa) also hold 1e-3; bf16 (7-bit) is judged on RMSE/SSIM instead
+# (tests/test_gpu_images.py) and only sanity-bounded here.
+TOL = {"fp32": 1e-4, "tf32": 1e-3, "fp16": 1e-3, "bf16": 2e-2}
+
+
+def _net(scale, seed, mode):
+    net = MODS[scale].CODONNet().eval().set_mode(mode)
+    net.load_state_dict(orc.synthetic_state_dict(scale, seed))
+    return net
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "fp16", "bf16"])
+@pytest.mark.parametrize("name", FWD)
+def test_forward_matches_reference(golden_dir, name, mode):
+    g = np.load(os.path.join(golden_dir, name))
+    net = _net(int(g["scale"]), int(g["seed"]), mode)
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    with torch.no_grad():
+        out = net(x, y)
+    torch.cuda.synchronize()
+    assert out.shape == x.shape and out.dtype == x.dtype
+    err = np.abs(out.cpu().numpy().astype(np.float64) - g["out_fp64"]).max()
+    print(f"{name} {mode}: max-abs {err:.3e}")
+    assert err <= TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16", "tf32"])
+def test_intermediate_taps_match_oracle(mode):
+    """Layer-level attribution: encoder, stage, fusion tensors vs the oracle's taps."""
+    sd = orc.synthetic_state_dict(4, 0)
+    x, y = orc.synthetic_frames(2, 45, 70, 7)
+    with torch.no_grad():
+        _, taps = orc.forward(sd, x, y, return_taps=True)
+    net = _net(4, 0, mode)
+    with torch.no_grad():
+        net(x.cuda(), y.cuda())
+    eng = net.engine(torch.device("cuda", 0))
+    rel = {"fp32": 1e-5, "tf32": 3e-3, "fp16": 3e-3, "bf16": 3e-2}[mode]
+    want = {"enc": torch.cat((taps["enc_d"], taps["enc_c"]), 1),
+            "feat": torch.cat((taps["out_d4"], taps["out_c4"]), 1),
+            "fuse": taps["fuse"], "out_fuse": taps["out_fuse"]}
+    for name, ref in want.items():
+        got = eng.debug_tap(name, 2, 45, 70).cpu()
+        scale = float(ref.abs().max())
+        err = float((got - ref).abs().max())
+        print(f"{mode} tap {name}: max-abs {err:.3e} (tensor max {scale:.3f})")
+        assert err <= rel * scale, (name, err, scale)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_half_io_like_reference_driver(dtype):
+    """model.cuda().half() with half frames (CODON_X4/test.py:52,122-123): mode follows the dtype."""
+    sd = orc.synthetic_state_dict(4, 1)
+    x, y = orc.synthetic_frames(1, 40, 56, 3)
+    net = CODON_x4.CODONNet().eval()
+    net.load_state_dict(sd)
+    net = net.cuda().to(dtype)
+    assert net.mode == {torch.float16: "fp16", torch.bfloat16: "bf16"}[dtype]
+    with torch.no_grad():
+        out = net(x.cuda().to(dtype), y.cuda().to(dtype))
+        ref = orc.forward(sd, x.to(dtype).float(), y.to(dtype).float())
+    assert out.dtype == dtype
+    tol = 4e-3 if dtype == torch.float16 else 3e-2
+    assert float((out.float().cpu() - ref).abs().max()) <= tol
+
+
+def test_batch_invariance_and_determinism():
+    """Frames are independent (CAC pools per sample): a frame's result does not depend on its batch
+    neighbours or on the run -- bit-exact."""
+    sd = orc.synthetic_state_dict(8, 2)
+    x, y = orc.synthetic_frames(3, 50, 66, 11)
+    for mode in ("fp32", "bf16"):
+        net = _net(8, 2, mode)
+        with torch.no_grad():
+            full = net(x.cuda(), y.cuda()).clone()
+            again = net(x.cuda(), y.cuda()).clone()
+            single = net(x[1:2].cuda(), y[1:2].cuda()).clone()
+        assert torch.equal(full, again)
+        assert torch.equal(full[1:2], single)
+
+
+def test_ragged_and_tiny_shapes():
+    sd = orc.synthetic_state_dict(4, 0)
+    net = _net(4, 0, "fp32")
+    netb = _net(4, 0, "fp16")
+    for (h, w) in [(1, 1), (3, 5), (17, 16), (16, 33), (65, 31)]:
+        x, y = orc.synthetic_frames(1, h, w, h * 100 + w)
+        with torch.no_grad():
+            ref = orc.forward(sd, x.double(), y.double()).float()
+            out = net(x.cuda(), y.cuda()).cpu()
+            outb = netb(x.cuda(), y.cuda()).cpu()
+        assert float((out - ref).abs().max()) <= 1e-4, (h, w)
+        assert float((outb - ref).abs().max()) <= 1e-3, (h, w)
+
+
+def test_host_entry_point_matches_device_entry_point():
+    sd = orc.synthetic_state_dict(4, 0)
+    x, y = orc.synthetic_frames(2, 33, 47, 5)
+    net = _net(4, 0, "fp16")
+    eng = net.engine(torch.device("cuda", 0))
+    with torch.no_grad():
+        dev = net(x.cuda(), y.cuda()).cpu().numpy()
+    host = eng.forward_host(x.numpy(), y.numpy())
+    np.testing.assert_array_equal(host, dev)
+    assert eng.last_launch_count >= 44
+
+
+def test_errors_are_loud():
+    net = _net(4, 0, "fp32")
+    x = torch.zeros(1, 1, 8, 8)
+    with pytest.raises(engine.CodonError):
+        net(x, x)                                   # CPU tensor
+    with pytest.raises(engine.CodonError):
+        net(x.cuda().expand(1, 2, 8, 8), x.cuda().expand(1, 2, 8, 8))   # not single-channel
+    eng = engine.Engine(4, "fp32", 0)
+    with pytest.raises(engine.CodonError):
+        eng.forward(x.cuda(), x.cuda())             # weights not loaded
+    with pytest.raises(engine.CodonError):
+        eng.load_state_dict({"conv1.weight": torch.zeros(3, 3)})        # wrong shape
+
+
+def test_full_size_linearity_property_free_checks():
+    """640x480 (BASELINE config 2): finite output, zero-weight output conv gives identity (global
+    residual, CODON_x4.py:131), and fp16/bf16 agree with fp32 mode."""
+    sd = orc.synthetic_state_dict(4, 0)
+    x, y = orc.synthetic_frames(1, 480, 640, 1234)
+    xc, yc = x.cuda(), y.cuda()
+    outs = {}
+    for mode in ("fp32", "fp16", "bf16", "tf32"):
+        net = _net(4, 0, mode)
+        with torch.no_grad():
+            outs[mode] = net(xc, yc)
+    assert torch.isfinite(outs["fp32"]).all()
+    for mode, tol in (("fp16", 1e-3), ("tf32", 1e-3), ("bf16", 2e-2)):
+        err = float((outs[mode] - outs["fp32"]).abs().max())
+        print(f"640x480 {mode} vs fp32 mode: {err:.3e}")
+        assert err <= tol
+    sd0 = dict(sd)
+    sd0["output.weight"] = torch.zeros_like(sd["output.weight"])
+    net = CODON_x4.CODONNet().eval().set_mode("bf16")
+    net.load_state_dict(sd0)
+    with torch.no_grad():
+        assert torch.equal(net(xc, yc), xc)
