@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the CODON forward pass on B200 (metric: HR depth megapixels per second).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                  [--mode tf32|fp32|fp16|bf16] [--scale 4|8|16] [--frames F] [--height H] [--width W]
+
+A step is one forward pass over one batch of F synthetic frames per GPU.  The default workload is
+BASELINE.json configs[1]: CODON x4, a single 640x480 frame, "fp32 parity mode" (mode tf32: fp32
+activations in HBM, TF32 tensor-core products, fp32 accumulation; max-abs error vs the reference
+fp32 forward <= 1e-3, measured in this run and printed under "parity").  With --gpus N>1 (launched
+under torchrun, one rank per GPU) every rank processes its own F frames per step: independent
+frames, no collective on the data path, weak scaling; NCCL is used for the barrier and the
+max-over-ranks timing only.
+
+One JSON line is printed by rank 0 (see the driver contract in the task description):
+  value        device-timed throughput, frames resident in HBM (CUDA events, max over ranks)
+  e2e          the same metric through the host entry point (codon_forward_host: pinned H2D of
+               the two frames + forward + D2H of the result inside the timed region)
+  roofline     dominant kernel (5x5 128->128 tcgen05 implicit GEMM): algorithmic FLOP / CUDA-event
+               time of its launches inside the timed region, against MEASURED_PEAKS.json
+  cpu_baseline the oracle's CPU forward (torch fp32, all host cores) on a bounded sample
+--impl reference times that CPU forward alone, as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "hr_depth_megapixels_per_second"
+UNIT = "MP/s"
+DTYPE_NAME = {"fp32": "f32", "tf32": "f32 (tf32 tensor-core products, f32 accumulate)",
+              "fp16": "f16 operands, f32 accumulate", "bf16": "bf16 operands, f32 accumulate"}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="codon_b200", choices=["codon_b200", "reference"])
+    ap.add_argument("--mode", default="tf32", choices=["fp32", "tf32", "fp16", "bf16"])
+    ap.add_argument("--scale", type=int, default=4, choices=[4, 8, 16])
+    ap.add_argument("--frames", type=int, default=1, help="frames per GPU per step")
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the other arithmetic modes")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"CODON x{a.scale}, {a.frames} x {a.width}x{a.height} synthetic RGB-D frame(s) per GPU per step, "
+            f"mode {a.mode}")
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU leg (oracle; the only place bench.py touches oracle/)
+
+def cpu_forward_sample(scale, height, width, budget_s, steps, warmup):
+    """Times the oracle's fp32 CPU forward (a functional restatement of the reference's PyTorch
+    forward; the reference itself is Python under /root/reference and cannot travel to the GPU box)
+    on a bounded sample: the top `rows` rows of one frame of the workload, rows chosen so that
+    (steps + warmup) forwards fit `budget_s`.  Returns (MP/s, description, cores, out, rows)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import codon_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = orc.synthetic_state_dict(scale, 0)
+    x, y = orc.synthetic_frames(1, height, width, 1234)
+    probe_rows = min(height, 96)
+    with torch.no_grad():
+        orc.forward(sd, x[:, :, :probe_rows], y[:, :, :probe_rows])          # oneDNN primitive warm-up
+        t0 = time.perf_counter()
+        orc.forward(sd, x[:, :, :probe_rows], y[:, :, :probe_rows])
+        rate = probe_rows * width / (time.perf_counter() - t0)               # px/s
+    rows = int(min(height, max(32, budget_s * rate / max(1, steps + warmup) / width)))
+    xs, ys = x[:, :, :rows].contiguous(), y[:, :, :rows].contiguous()
+    times, out = [], None
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = orc.forward(sd, xs, ys)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    mean_s = sum(times) / len(times)
+    desc = (f"{steps} timed forward(s) after {warmup} warm-up on the top {rows} of {height} rows of one "
+            f"{width}x{height} frame (x{scale} synthetic weights seed 0, torch {torch.__version__} fp32, {cores} threads)")
+    return rows * width / 1e6 / mean_s, desc, cores, out, rows, mean_s
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, a.steps), max(0, a.warmup)
+    mps, desc, cores, _, rows, mean_s = cpu_forward_sample(a.scale, a.height, a.width, 150.0, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mps, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "timing": "host wall clock around the CPU forward"},
+        "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": mps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+
+def time_mode(eng, x, y, out, steps, warmup, flush, dist_barrier, profile=False):
+    """Device time of `steps` forwards (CUDA events on the current stream, L2 flushed between steps)."""
+    import torch
+    for _ in range(warmup):
+        eng.forward(x, y, out)
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    if profile:
+        eng.profile_reset()
+        eng.profile_enable(True)
+    dist_barrier()
+    torch.cuda.synchronize()
+    for i in range(steps):
+        flush.zero_()                      # evict L2 (buffer larger than the 126 MB L2), outside the timed window
+        starts[i].record()
+        eng.forward(x, y, out)
+        ends[i].record()
+    torch.cuda.synchronize()
+    dist_barrier()
+    prof = None
+    if profile:
+        eng.profile_enable(False)
+        prof = eng.profile_read()
+    return sum(s.elapsed_time(e) for s, e in zip(starts, ends)), prof
+
+
+def run_gpu(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from codon_b200 import engine as E, synthetic as syn, build
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; codon_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    build.build_library()
+    peaks = load_peaks()
+    B, H, W = a.frames, a.height, a.width
+    P = B * H * W
+    sd = syn.synthetic_state_dict(a.scale, 0)
+    # every rank gets its own frames (seed offset by rank): independent shards, no data-path collective
+    xh, yh = syn.synthetic_frames(B, H, W, 1234 + rank * B)
+    x, y = xh.to(dev), yh.to(dev)
+    out = torch.empty_like(x)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    steps, warmup = max(1, a.steps), max(3, a.warmup)
+
+    eng = E.Engine(a.scale, a.mode, local)
+    eng.load_state_dict(sd)
+
+    # ---- device-timed throughput + per-kernel-class profile ---------------------------------------
+    with ClockSampler(local) as clk:
+        total_ms, prof = time_mode(eng, x, y, out, steps, warmup, flush, barrier, profile=True)
+        launches = eng.last_launch_count * steps
+        # ---- end to end through the host entry point (pinned H2D + forward + D2H per step) -----------
+        xn, yn = xh.numpy(), yh.numpy()
+        for _ in range(2):
+            eng.forward_host(xn, yn)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = eng.forward_host(xn, yn)
+        e2e_s = time.perf_counter() - t0
+        barrier()
+    total_ms = max_over_ranks(total_ms)
+    e2e_s = max_over_ranks(e2e_s)
+    value = world * P * steps / 1e6 / (total_ms / 1e3)
+    e2e_value = world * P * steps / 1e6 / e2e_s
+    assert np.isfinite(res).all()
+
+    # ---- roofline of the dominant kernel (measured live above) --------------------------------------
+    dom = prof["conv5x5_128to128"]
+    tfs = dom["work"] / (dom["ms"] / 1e3) / 1e12 if dom["ms"] > 0 else 0.0
+    conv_ms = sum(prof[k]["ms"] for k in ("conv5x5_128to128", "pair_3x3_5x5_64to128", "conv3x3", "conv1x1_128to64"))
+    cac_ms = prof["cac_stats"]["ms"] + prof["cac_apply"]["ms"]
+    cac_bytes = prof["cac_stats"]["work"] + prof["cac_apply"]["work"]
+    all_ms = sum(v["ms"] for v in prof.values())
+    peak_tf = peaks["bf16_tflops"]
+    roofline = {
+        "kernel": "conv_tc_kernel (5x5 128->128 implicit GEMM, tcgen05)", "bound": "tensor",
+        "achieved": tfs, "peak": peak_tf, "unit": "TFLOP/s", "frac": tfs / peak_tf, "traffic": None,
+        "peak_source": peaks["source"] + ", dense bf16 burst" +
+                       ("; tf32 runs at half the bf16 rate, so frac <= 0.5 in this mode" if a.mode == "tf32" else ""),
+        "flop_per_launch": dom["work"] / max(1, dom["launches"]), "ms_per_launch": dom["ms"] / max(1, dom["launches"]),
+        "launches": dom["launches"], "share_of_step": dom["ms"] / all_ms if all_ms else None,
+        "trunk_all_convs": {"achieved": syn.FLOPS_PER_PIXEL * P * steps / (conv_ms / 1e3) / 1e12 if conv_ms else None,
+                            "unit": "TFLOP/s", "ms_per_step": conv_ms / steps},
+        "cac_kernels": {"bound": "hbm", "achieved": cac_bytes / (cac_ms / 1e3) / 1e9 if cac_ms else None,
+                        "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": cac_bytes / (cac_ms / 1e3) / 1e9 / peaks["hbm_gbs"] if cac_ms else None,
+                        "ms_per_step": cac_ms / steps},
+        "by_kernel_ms_per_step": {k: v["ms"] / steps for k, v in prof.items()},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": DTYPE_NAME[a.mode], "data": "synthetic",
+        "config": {"workload": workload_name(a), "scale": a.scale, "frames_per_gpu": B, "height": H, "width": W,
+                   "mode": a.mode, "weights": "synthetic seed 0 (reference init, output.weight x0.002)",
+                   "sharding": "independent frames per rank, no data-path collective",
+                   "l2": "256 MiB buffer written between timed steps (L2 flush, outside the event window)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * P * 4, "d2h_bytes_per_step": P * 4,
+                "api": "Engine.forward_host -> codon_forward_host (host fp32 frames in, host fp32 depth out)"},
+        "gpu_launches": launches, "roofline": roofline, "clocks": clk.summary(),
+    }
+
+    if rank == 0 and world == 1:
+        # ---- other arithmetic modes on the same workload (reported, not the headline) ---------------
+        if not a.no_variants:
+            variants = {}
+            outs = {a.mode: out.clone()}
+            for m in ("fp32", "tf32", "fp16", "bf16"):
+                if m == a.mode:
+                    continue
+                e2 = E.Engine(a.scale, m, local)
+                e2.load_state_dict(sd)
+                o2 = torch.empty_like(x)
+                k = steps if m != "fp32" else max(2, steps // 5)
+                ms, _ = time_mode(e2, x, y, o2, k, 3, flush, barrier)
+                variants[m] = {"value": P * k / 1e6 / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / k}
+                outs[m] = o2.clone()
+                e2.close()
+            line["variants"] = variants
+        else:
+            outs = {a.mode: out.clone()}
+        # ---- CPU baseline (oracle) on a bounded sample + parity of the GPU result against it --------
+        if not a.no_cpu_baseline:
+            mps, desc, cores, ref, rows, _ = cpu_forward_sample(a.scale, H, W, 20.0, 1, 1)
+            line["cpu_baseline"] = {"value": mps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+            # The sample is the top `rows` rows; the receptive field is 47 px and the CAC
+            # pooling is global, so compare the GPU forward of the SAME cropped input.
+            xs, ys = x[:1, :, :rows].contiguous(), y[:1, :, :rows].contiguous()
+            par = {}
+            for m in outs:
+                e2 = E.Engine(a.scale, m, local)
+                e2.load_state_dict(sd)
+                o = e2.forward(xs, ys)
+                torch.cuda.synchronize()
+                par[m] = float((o.cpu() - ref).abs().max())
+                e2.close()
+            line["parity"] = {"max_abs_err_vs_cpu_oracle": par, "tolerance_fp32_mode": 1e-3,
+                              "input": f"top {rows} rows of frame 0"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_gpu(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -85,6 +85,14 @@ struct codon_ctx {
   };
   std::map<MapKey, CUtensorMap> tmaps;
 
+  // per-category CUDA-event profiling of the launches (bench.py roofline)
+  bool prof_on = false;
+  struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[8] = {}, prof_work[8] = {};
+  long long prof_n[8] = {};
+
   // last forward (debug taps)
   uint8_t* last_ws = nullptr;
   Buffers last_buf;
@@ -118,6 +126,27 @@ int fail(codon_ctx* ctx, int code, const char* fmt, ...) {
   } while (0)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+enum ProfCat { PC_CONV5_128 = 0, PC_PAIR = 1, PC_CONV3 = 2, PC_CONV1 = 3, PC_EDGE = 4, PC_CAC_STATS = 5, PC_CAC_MLP = 6, PC_CAC_APPLY = 7 };
+const char* const kProfNames[8] = {"conv5x5_128to128", "pair_3x3_5x5_64to128", "conv3x3", "conv1x1_128to64", "edge_1to64_64to1",
+                                   "cac_stats", "cac_mlp", "cac_apply"};
+
+// Scoped event pair around one launch (no-op unless profiling is enabled on the context).
+struct ProfScope {
+  codon_ctx* ctx; cudaStream_t st; cudaEvent_t b = nullptr;
+  ProfScope(codon_ctx* c, int cat, double work, cudaStream_t s) : ctx(c), st(s) {
+    if (!ctx->prof_on) return;
+    cudaEvent_t ev[2];
+    for (auto& e : ev) {
+      if (ctx->prof_pool.empty()) { if (cudaEventCreate(&e) != cudaSuccess) return; }
+      else { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+    }
+    cudaEventRecord(ev[0], st);
+    b = ev[1];
+    ctx->prof_recs.push_back({ev[0], ev[1], cat, work});
+  }
+  ~ProfScope() { if (b) cudaEventRecord(b, st); }
+};
 
 Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W) {
   Buffers b;
@@ -194,6 +223,7 @@ struct Runner {
 
   int conv(const char* plan_name, size_t in, int in_C, int cin, int cout, int ks, bool relu,
            const LayerJob* jobs, int njobs) {
+    const double flops = 2.0 * B * H * W * (double)cin * cout * ks * ks * njobs;
     if (ctx->mode == CODON_MODE_FP32) {
       ConvJob cj[2];
       for (int i = 0; i < njobs; ++i) {
@@ -203,6 +233,7 @@ struct Runner {
         cj[i].res = jobs[i].has_res ? ws + jobs[i].res : nullptr;
         cj[i].res_stride = jobs[i].res_stride; cj[i].res_off = jobs[i].res_off;
       }
+      ProfScope ps(ctx, cat_of(cin, cout, ks), flops, st);
       CU_TRY(ctx, launch_conv_direct_f32(cj, njobs, B, H, W, cin, cout, ks, relu, st));
       ctx->launches++;
       return CODON_OK;
@@ -224,9 +255,17 @@ struct Runner {
     const CUtensorMap* tm = nullptr;
     int rc = get_tmap(ctx, ws + in, in_C, tc_box_rows(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
     if (rc) return rc;
+    ProfScope ps(ctx, cat_of(cin, cout, ks), flops, st);
     CU_TRY(ctx, launch_conv_tc(*tm, l0.plan, L, st));
     ctx->launches++;
     return CODON_OK;
+  }
+
+  static int cat_of(int cin, int cout, int ks) {
+    if (ks == 5 && cin == 128) return PC_CONV5_128;
+    if (ks == 1) return PC_CONV1;
+    if (ks == 5) return PC_PAIR;      // fp32 mode runs the pair as separate 3x3 / 5x5 launches
+    return PC_CONV3;
   }
 
   // 3x3 || 5x5 multi-scale pair on a 64-channel input slice -> 128 output channels at out_off.
@@ -259,6 +298,7 @@ struct Runner {
     const CUtensorMap* tm = nullptr;
     int rc = get_tmap(ctx, ws + in, in_C, tc_box_rows(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
     if (rc) return rc;
+    ProfScope ps(ctx, PC_PAIR, 2.0 * B * H * W * 64.0 * 64.0 * 34.0 * njobs, st);
     CU_TRY(ctx, launch_conv_tc(*tm, l0.plan, L, st));
     ctx->launches++;
     return CODON_OK;
@@ -271,7 +311,11 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
   int rc;
   // encoders (CODON_x4.py:68-73): input/input_c 1->64 (+ReLU) into the R2 region viewed as 128 ch
   const size_t T0 = bf.R2;
-  CU_TRY(ctx, launch_conv_first(x, y, ctx->w_in_d, ctx->w_in_c, ws + T0, ctx->act, B, H, W, st));
+  const double P = (double)B * H * W;
+  {
+    ProfScope ps(ctx, PC_EDGE, P * (8 + 128 * r.e), st);
+    CU_TRY(ctx, launch_conv_first(x, y, ctx->w_in_d, ctx->w_in_c, ws + T0, ctx->act, B, H, W, st, ctx->mode == CODON_MODE_TF32));
+  }
   ctx->launches++;
   {
     LayerJob j[2] = {{"conv_input", 0, bf.E, 128, 0, 0, 0, 0, false}, {"conv_input_c", 64, bf.E, 128, 64, 0, 0, 0, false}};
@@ -299,10 +343,20 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     float* pooled = reinterpret_cast<float*>(ws + bf.pooled);
     float* part = reinterpret_cast<float*>(ws + bf.part);
     float* sc = reinterpret_cast<float*>(ws + bf.sc);
-    CU_TRY(ctx, launch_cac_stats(ws + bf.F, ctx->act, B, H, W, pooled, part, bf.chunks, st));
-    CU_TRY(ctx, launch_cac_mlp(part, bf.chunks, B, H * W, ctx->cac_w1[s], ctx->cac_b1[s], ctx->cac_w2[s],
-                               ctx->cac_b2[s], sc, st));
-    CU_TRY(ctx, launch_cac_apply(ws + bf.F, ws + bf.E, ctx->act, pooled, sc, ctx->cac_ws[s], B, H, W, st));
+    // algorithmic HBM bytes: stats reads F (128e B/px); apply reads F and E, writes F (384e B/px)
+    {
+      ProfScope ps(ctx, PC_CAC_STATS, P * 128 * r.e, st);
+      CU_TRY(ctx, launch_cac_stats(ws + bf.F, ctx->act, B, H, W, pooled, part, bf.chunks, st));
+    }
+    {
+      ProfScope ps(ctx, PC_CAC_MLP, 0.0, st);
+      CU_TRY(ctx, launch_cac_mlp(part, bf.chunks, B, H * W, ctx->cac_w1[s], ctx->cac_b1[s], ctx->cac_w2[s],
+                                 ctx->cac_b2[s], sc, st));
+    }
+    {
+      ProfScope ps(ctx, PC_CAC_APPLY, P * 384 * r.e, st);
+      CU_TRY(ctx, launch_cac_apply(ws + bf.F, ws + bf.E, ctx->act, pooled, sc, ctx->cac_ws[s], B, H, W, st, ctx->mode == CODON_MODE_TF32));
+    }
     ctx->launches += 3;
   }
   // fusion head (:119-121): cat(out, out_c) is F itself
@@ -333,7 +387,10 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     LayerJob j[1] = {{"conv11", 0, bf.MS, 64, 0, 0, 0, 0, false}};
     if ((rc = r.conv("", bf.OF, 64, 64, 64, 3, true, j, 1))) return rc;
   }
-  CU_TRY(ctx, launch_conv_last(ws + bf.MS, 64, ctx->act, ctx->w_out, x, out, B, H, W, st));
+  {
+    ProfScope ps(ctx, PC_EDGE, P * (8 + 64 * r.e), st);
+    CU_TRY(ctx, launch_conv_last(ws + bf.MS, 64, ctx->act, ctx->w_out, x, out, B, H, W, st));
+  }
   ctx->launches++;
   return CODON_OK;
 }
@@ -382,6 +439,8 @@ void codon_destroy(codon_ctx* ctx) {
   if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
   if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
   if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
+  for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -586,6 +645,45 @@ int codon_forward_host(codon_ctx* ctx, const float* depth, const float* guide, f
 }
 
 int codon_last_launch_count(const codon_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int codon_profile_enable(codon_ctx* ctx, int on) {
+  if (!ctx) return fail(nullptr, CODON_ERR_ARG, "codon_profile_enable: ctx is NULL");
+  ctx->prof_on = on != 0;
+  return CODON_OK;
+}
+
+static int prof_collect(codon_ctx* ctx) {
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (auto& r : ctx->prof_recs) {
+    CU_TRY(ctx, cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, r.a, r.b));
+    ctx->prof_ms[r.cat] += ms; ctx->prof_work[r.cat] += r.work; ctx->prof_n[r.cat]++;
+    ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b);
+  }
+  ctx->prof_recs.clear();
+  return CODON_OK;
+}
+
+int codon_profile_read(codon_ctx* ctx, int category, double* total_ms, double* work, long long* launches) {
+  if (!ctx || category < 0 || category >= 8) return fail(ctx, CODON_ERR_ARG, "codon_profile_read: bad argument");
+  int rc = prof_collect(ctx);
+  if (rc) return rc;
+  if (total_ms) *total_ms = ctx->prof_ms[category];
+  if (work) *work = ctx->prof_work[category];
+  if (launches) *launches = ctx->prof_n[category];
+  return CODON_OK;
+}
+
+int codon_profile_reset(codon_ctx* ctx) {
+  if (!ctx) return fail(nullptr, CODON_ERR_ARG, "codon_profile_reset: ctx is NULL");
+  int rc = prof_collect(ctx);
+  if (rc) return rc;
+  for (int i = 0; i < 8; ++i) { ctx->prof_ms[i] = 0; ctx->prof_work[i] = 0; ctx->prof_n[i] = 0; }
+  return CODON_OK;
+}
+
+const char* codon_profile_category_name(int category) { return category >= 0 && category < 8 ? kProfNames[category] : ""; }
 
 int codon_debug_tap(codon_ctx* ctx, const char* name, float* dst, int* channels, void* cuda_stream) {
   if (!ctx || !name || !dst || !channels) return fail(ctx, CODON_ERR_ARG, "codon_debug_tap: bad argument");

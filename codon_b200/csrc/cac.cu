@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) cac_apply_kernel(T* __restrict__ F, const
                                                         const float* __restrict__ pooled,
                                                         const float* __restrict__ sc,
                                                         const float* __restrict__ ws, int H, int W,
-                                                        int tiles_x) {
+                                                        int tiles_x, int rnd_tf32) {
   constexpr int V = Act<T>::kVec, LPP = 128 / V, PH = kATH + 4, PW = kATW + 4;
   __shared__ float2 sp[PH][PW];
   __shared__ float sw[50], ssc[64], sss[kATH * kATW];
@@ -178,6 +178,10 @@ __global__ void __launch_bounds__(256) cac_apply_kernel(T* __restrict__ F, const
       const int c0 = (g * V) & 63;
 #pragma unroll
       for (int j = 0; j < V; ++j) f[j] = fmaf(f[j], ssc[c0 + j] * s, e[j]);
+      if (rnd_tf32) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) f[j] = round_tf32(f[j]);
+      }
       Act<T>::store(F + o, f);
     }
   }
@@ -204,12 +208,12 @@ cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const f
 }
 
 cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* pooled, const float* sc,
-                             const float* ws, int B, int H, int W, cudaStream_t st) {
+                             const float* ws, int B, int H, int W, cudaStream_t st, int rnd_tf32) {
   const int tiles_x = cdiv(W, kATW);
   dim3 grid(tiles_x * cdiv(H, kATH), B);
-  if (act == ACT_F32) cac_apply_kernel<float><<<grid, 256, 0, st>>>((float*)F, (const float*)E, pooled, sc, ws, H, W, tiles_x);
-  else if (act == ACT_BF16) cac_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)F, (const __nv_bfloat16*)E, pooled, sc, ws, H, W, tiles_x);
-  else cac_apply_kernel<__half><<<grid, 256, 0, st>>>((__half*)F, (const __half*)E, pooled, sc, ws, H, W, tiles_x);
+  if (act == ACT_F32) cac_apply_kernel<float><<<grid, 256, 0, st>>>((float*)F, (const float*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32);
+  else if (act == ACT_BF16) cac_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)F, (const __nv_bfloat16*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32);
+  else cac_apply_kernel<__half><<<grid, 256, 0, st>>>((__half*)F, (const __half*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32);
   return cudaGetLastError();
 }
 

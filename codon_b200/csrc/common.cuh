@@ -72,6 +72,14 @@ template <> struct Act<__half> {
   __device__ static inline __half from_float(float v) { return __float2half_rn(v); }
 };
 
+// Round-to-nearest fp32 -> tf32 (10-bit mantissa), kept in an fp32 container.  The TF32 MMA
+// ignores the low 13 mantissa bits (truncation); rounding at the producer halves that error.
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
 __device__ __forceinline__ float sigmoidf_exact(float z) { return 1.0f / (1.0f + expf(-z)); }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }

@@ -162,7 +162,7 @@ __device__ __forceinline__ Tile decode_tile(const TcKParams& p, int t, int tile_
 // Epilogue of one 32-channel chunk held by one thread (one pixel).
 template <typename T>
 __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], const TcJob& job, size_t pix, int c0,
-                                            bool relu) {
+                                            bool relu, bool rnd_tf32 = false) {
   constexpr int V = Act<T>::kVec;
   T* out = static_cast<T*>(job.out) + pix * job.out_stride + job.out_off + c0;
   const T* res = job.res ? static_cast<const T*>(job.res) + pix * job.res_stride + job.res_off + c0 : nullptr;
@@ -179,6 +179,10 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], const TcJob
       Act<T>::load(res + v * V, e);
 #pragma unroll
       for (int j = 0; j < V; ++j) f[j] += e[j];
+    }
+    if (rnd_tf32) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) f[j] = round_tf32(f[j]);
     }
     Act<T>::store(out + v * V, f);
   }
@@ -329,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r);
           tmem_ld_wait();
           if (valid) {
-            if (p.out_act == ACT_F32) store_chunk<float>(r, job, pix, c0, p.relu != 0);
+            if (p.out_act == ACT_F32) store_chunk<float>(r, job, pix, c0, p.relu != 0, p.is_tf32 != 0);
             else if (p.out_act == ACT_BF16) store_chunk<__nv_bfloat16>(r, job, pix, c0, p.relu != 0);
             else store_chunk<__half>(r, job, pix, c0, p.relu != 0);
           }

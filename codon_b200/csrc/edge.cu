@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
                                                          const float* __restrict__ y,
                                                          const float* __restrict__ w_d,
                                                          const float* __restrict__ w_c,
-                                                         T* __restrict__ out, int B, int H, int W) {
+                                                         T* __restrict__ out, int B, int H, int W, int rnd_tf32) {
   constexpr int V = Act<T>::kVec, LPP = 128 / V;   // lanes per pixel
   __shared__ float sw[2][9][64];
   for (int i = threadIdx.x; i < 2 * 9 * 64; i += blockDim.x)
@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 #pragma unroll
       for (int t = 0; t < 9; ++t) a = fmaf(in[t], sw[br][t][c + j], a);
       v[j] = fmaxf(a, 0.f);
+      if (rnd_tf32) v[j] = round_tf32(v[j]);
     }
     Act<T>::store(out + pix * 128 + c0, v);
   }
@@ -127,14 +128,14 @@ inline int grid_for(size_t total, int block) {
 }  // namespace
 
 cudaError_t launch_conv_first(const float* x, const float* y, const float* w_d, const float* w_c,
-                              void* out, int act, int B, int H, int W, cudaStream_t st) {
+                              void* out, int act, int B, int H, int W, cudaStream_t st, int rnd_tf32) {
   const size_t pix = (size_t)B * H * W;
   if (act == ACT_F32)
-    conv_first_kernel<float><<<grid_for(pix * 32, 256), 256, 0, st>>>(x, y, w_d, w_c, (float*)out, B, H, W);
+    conv_first_kernel<float><<<grid_for(pix * 32, 256), 256, 0, st>>>(x, y, w_d, w_c, (float*)out, B, H, W, rnd_tf32);
   else if (act == ACT_BF16)
-    conv_first_kernel<__nv_bfloat16><<<grid_for(pix * 16, 256), 256, 0, st>>>(x, y, w_d, w_c, (__nv_bfloat16*)out, B, H, W);
+    conv_first_kernel<__nv_bfloat16><<<grid_for(pix * 16, 256), 256, 0, st>>>(x, y, w_d, w_c, (__nv_bfloat16*)out, B, H, W, 0);
   else
-    conv_first_kernel<__half><<<grid_for(pix * 16, 256), 256, 0, st>>>(x, y, w_d, w_c, (__half*)out, B, H, W);
+    conv_first_kernel<__half><<<grid_for(pix * 16, 256), 256, 0, st>>>(x, y, w_d, w_c, (__half*)out, B, H, W, 0);
   return cudaGetLastError();
 }
 

@@ -26,7 +26,7 @@ cudaError_t launch_conv_direct_f32(const ConvJob* jobs, int njobs, int B, int H,
 // input / input_c: 1 -> 64, 3x3, ReLU (CODON_x4.py:68,71).  x, y fp32 [B,H,W]; w_d, w_c fp32
 // [9][64]; out NHWC 128 ch (depth | colour) of type act.
 cudaError_t launch_conv_first(const float* x, const float* y, const float* w_d, const float* w_c,
-                              void* out, int act, int B, int H, int W, cudaStream_t st);
+                              void* out, int act, int B, int H, int W, cudaStream_t st, int rnd_tf32 = 0);
 // output: 64 -> 1, 3x3, + global residual x (CODON_x4.py:130-131).  in NHWC 64 ch of type act
 // (pixel stride in_stride); w fp32 [9][64]; x, out fp32 [B,H,W].
 cudaError_t launch_conv_last(const void* in, int in_stride, int act, const float* w, const float* x,
@@ -46,7 +46,7 @@ cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const f
 // apply: F = F * sc[b, c % 64] * sigmoid(conv5x5(pooled))[b,h,w] + E   (in place on F).
 // ws fp32 [2][25] (max map taps, then mean map taps).
 cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* pooled, const float* sc,
-                             const float* ws, int B, int H, int W, cudaStream_t st);
+                             const float* ws, int B, int H, int W, cudaStream_t st, int rnd_tf32 = 0);
 
 // ---- utility -------------------------------------------------------------------------------------
 cudaError_t launch_convert_to_f32(const void* src, int dtype, float* dst, size_t n, cudaStream_t st);

@@ -23,7 +23,8 @@ _IO_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 ABI_SYMBOLS = [
     "codon_create", "codon_destroy", "codon_last_error", "codon_version", "codon_set_weight",
     "codon_finalize_weights", "codon_workspace_bytes", "codon_forward", "codon_forward_host",
-    "codon_last_launch_count", "codon_debug_tap", "codon_cac_channel", "codon_cac_spatial",
+    "codon_last_launch_count", "codon_debug_tap", "codon_profile_enable", "codon_profile_read",
+    "codon_profile_reset", "codon_profile_category_name", "codon_cac_channel", "codon_cac_spatial",
     "codon_cac_apply", "codon_channel_stats", "codon_channel_pool", "codon_conv2d_nchw",
     "codon_masked_rmse", "codon_ssim_gauss", "codon_quantise_u8",
 ]
@@ -65,6 +66,11 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         lib.codon_forward_host.argtypes = [vp, vp, vp, vp, ip, ip, ip]
         lib.codon_last_launch_count.argtypes = [vp]
         lib.codon_debug_tap.argtypes = [vp, c.c_char_p, vp, c.POINTER(ip), vp]
+        lib.codon_profile_enable.argtypes = [vp, ip]
+        lib.codon_profile_read.argtypes = [vp, ip, c.POINTER(c.c_double), c.POINTER(c.c_double), c.POINTER(c.c_longlong)]
+        lib.codon_profile_reset.argtypes = [vp]
+        lib.codon_profile_category_name.argtypes = [ip]
+        lib.codon_profile_category_name.restype = c.c_char_p
         lib.codon_cac_channel.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, vp, ip, ip, ip, vp, vp]
         lib.codon_cac_spatial.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, vp]
         lib.codon_cac_apply.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, ip, vp, vp]
@@ -76,7 +82,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         lib.codon_quantise_u8.argtypes = [vp, vp, c.c_size_t, ip, vp]
         for name in ABI_SYMBOLS:
             fn = getattr(lib, name)
-            if name not in ("codon_destroy", "codon_last_error", "codon_version", "codon_workspace_bytes"):
+            if name not in ("codon_destroy", "codon_last_error", "codon_version", "codon_workspace_bytes",
+                            "codon_profile_category_name"):
                 fn.restype = c.c_int
         if path is None:
             _lib = lib
@@ -199,6 +206,22 @@ class Engine:
     @property
     def last_launch_count(self) -> int:
         return int(self.lib.codon_last_launch_count(self._ctx))
+
+    # ---- per-kernel-class profiling (CUDA events on the forward's stream) ---------------------------
+    def profile_enable(self, on: bool = True) -> None:
+        check(self.lib.codon_profile_enable(self._ctx, int(on)), self._ctx)
+
+    def profile_reset(self) -> None:
+        check(self.lib.codon_profile_reset(self._ctx), self._ctx)
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        """{category: {"ms": total device ms, "work": FLOP or bytes, "launches": n}} since the last reset."""
+        out = {}
+        for cat in range(8):
+            ms, work, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_longlong(0)
+            check(self.lib.codon_profile_read(self._ctx, cat, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(n)), self._ctx)
+            out[self.lib.codon_profile_category_name(cat).decode()] = {"ms": ms.value, "work": work.value, "launches": int(n.value)}
+        return out
 
     def debug_tap(self, name: str, B: int, H: int, W: int) -> torch.Tensor:
         chans = {"enc": 128, "feat": 128, "ms": 256, "fuse": 64, "out_fuse": 64}[name]

@@ -101,6 +101,17 @@ int codon_forward_host(codon_ctx* ctx, const float* depth, const float* guide, f
 /* Number of kernels the last codon_forward on this context launched. */
 int codon_last_launch_count(const codon_ctx* ctx);
 
+/* Per-kernel-class timing of the launches codon_forward makes, with CUDA events recorded on the
+ * forward's own stream (what bench.py's roofline is computed from).  Categories 0..7:
+ * conv5x5_128to128, pair_3x3_5x5_64to128, conv3x3, conv1x1_128to64, edge_1to64_64to1, cac_stats,
+ * cac_mlp, cac_apply.  codon_profile_read waits for the recorded events and returns the totals
+ * accumulated since the last reset: device milliseconds, algorithmic work (FLOP for the convs,
+ * HBM bytes for edge / CAC kernels) and the number of launches. */
+int codon_profile_enable(codon_ctx* ctx, int on);
+int codon_profile_read(codon_ctx* ctx, int category, double* total_ms, double* work, long long* launches);
+int codon_profile_reset(codon_ctx* ctx);
+const char* codon_profile_category_name(int category);
+
 /* Copies an intermediate activation of the last forward to dst as fp32 NCHW [B,C,H,W]
  * (DEVICE pointer, C returned through channels).  Names: "enc" (128: depth|colour encoder
  * outputs), "feat" (128: depth|colour stage outputs after the last stage), "ms" (256),

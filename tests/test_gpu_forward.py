@@ -53,7 +53,7 @@ def test_intermediate_taps_match_oracle(mode):
     with torch.no_grad():
         net(x.cuda(), y.cuda())
     eng = net.engine(torch.device("cuda", 0))
-    rel = {"fp32": 1e-5, "tf32": 3e-3, "fp16": 3e-3, "bf16": 3e-2}[mode]
+    rel = {"fp32": 1e-5, "tf32": 6e-3, "fp16": 3e-3, "bf16": 3e-2}[mode]
     want = {"enc": torch.cat((taps["enc_d"], taps["enc_c"]), 1),
             "feat": torch.cat((taps["out_d4"], taps["out_c4"]), 1),
             "fuse": taps["fuse"], "out_fuse": taps["out_fuse"]}
