@@ -24,6 +24,7 @@
 //     persistent CTAs stride over the tile list.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include "common.cuh"
 #include "kernels.h"
@@ -48,6 +49,7 @@ struct TcKParams {
   uint32_t idesc_full, idesc_half;
   int relu, out_act, is_tf32, nbuf;
   uint32_t patch_tx;
+  int debug;   // CODON_TC_DEBUG bits (perf experiments only): 1 no epilogue stores, 2 no B loads, 4 no A loads, 8 no MMAs
 };
 
 template <int NACC> struct TcCfg {
@@ -104,6 +106,18 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// One lane of a converged warp (the canonical way to issue tcgen05 / TMA instructions: the
+// surrounding control flow stays warp-uniform, so the compiler emits plain uniform-datapath
+// UTCHMMA / UTMALDG instead of a per-thread "waterfall" loop around each of them).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -145,6 +159,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int OPERAND> struct OperandTraits;
+template <> struct OperandTraits<TC_F16> { using Out = __half; };
+template <> struct OperandTraits<TC_BF16> { using Out = __nv_bfloat16; };
+template <> struct OperandTraits<TC_TF32> { using Out = float; };
 
 struct Tile { int job, n, y0, x0; };
 __device__ __forceinline__ Tile decode_tile(const TcKParams& p, int t, int tile_h) {
@@ -188,9 +207,10 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], const TcJob
   }
 }
 
-template <int NACC>
+template <int NACC, int OPERAND>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcKParams p) {
+  using OutT = typename OperandTraits<OPERAND>::Out;
   using Cfg = TcCfg<NACC>;
   constexpr int NPB = Cfg::kPatchStages;
   constexpr int TILE_H = NACC * kTcRowsPerAcc;
@@ -229,84 +249,96 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ================================ producer ================================================
-    if (lane == 0) {
-      int ps = 0, bs = 0;
-      uint32_t pph = 0, bph = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const Tile tl = decode_tile(p, t, TILE_H);
-        const TcJob& job = p.job[tl.job];
-        for (int s = 0; s < p.nslab; ++s) {
-          const uint8_t* wslab = job.w + (size_t)s * p.slab_bytes;
-          for (int dxi = 0; dxi < p.ndx; ++dxi) {
-            mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
-            mbar_expect_tx(bar_patch_full + 8 * ps, p.patch_tx);
-            tma_load_4d(s_patch + ps * Cfg::kPatchBytes, &tmap, bar_patch_full + 8 * ps,
-                        job.in_coff + s * p.slab_elems, tl.x0 + p.dx_ord[dxi] - p.pad, tl.y0 - p.pad, tl.n);
-            if (++ps == NPB) { ps = 0; pph ^= 1; }
-            for (int dyi = 0; dyi < p.ndy; ++dyi) {
-              mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
-              const uint32_t bytes = p.b_bytes[dxi][dyi];
-              mbar_expect_tx(bar_b_full + 8 * bs, bytes);
-              bulk_load(s_b + bs * kBStageBytes, wslab + p.b_off[dxi][dyi], bytes, bar_b_full + 8 * bs);
-              if (++bs == kBStages) { bs = 0; bph ^= 1; }
+    // ================================ producer (warp-uniform loops, one elected lane issues) ====
+    int ps = 0, bs = 0;
+    uint32_t pph = 0, bph = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const Tile tl = decode_tile(p, t, TILE_H);
+      const TcJob& job = p.job[tl.job];
+      for (int s = 0; s < p.nslab; ++s) {
+        const uint8_t* wslab = job.w + (size_t)s * p.slab_bytes;
+        for (int dxi = 0; dxi < p.ndx; ++dxi) {
+          mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
+          if (elect_one()) {
+            if (p.debug & 4) mbar_arrive(bar_patch_full + 8 * ps);
+            else {
+              mbar_expect_tx(bar_patch_full + 8 * ps, p.patch_tx);
+              tma_load_4d(s_patch + ps * Cfg::kPatchBytes, &tmap, bar_patch_full + 8 * ps,
+                          job.in_coff + s * p.slab_elems, tl.x0 + p.dx_ord[dxi] - p.pad, tl.y0 - p.pad, tl.n);
             }
+          }
+          __syncwarp();
+          if (++ps == NPB) { ps = 0; pph ^= 1; }
+          for (int dyi = 0; dyi < p.ndy; ++dyi) {
+            mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
+            if (elect_one()) {
+              const uint32_t bytes = p.b_bytes[dxi][dyi];
+              if (p.debug & 2) mbar_arrive(bar_b_full + 8 * bs);
+              else {
+                mbar_expect_tx(bar_b_full + 8 * bs, bytes);
+                bulk_load(s_b + bs * kBStageBytes, wslab + p.b_off[dxi][dyi], bytes, bar_b_full + 8 * bs);
+              }
+            }
+            __syncwarp();
+            if (++bs == kBStages) { bs = 0; bph ^= 1; }
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ================================ MMA issuer ==============================================
-    if (lane == 0) {
-      int ps = 0, bs = 0;
-      uint32_t pph = 0, bph = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        const Tile tl = decode_tile(p, t, TILE_H);
-        const TcJob& job = p.job[tl.job];
-        const int buf = it % p.nbuf;
-        const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
-        mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
-        tc_fence_after();
-        const uint32_t d_base = tmem_base + (uint32_t)(buf * NACC * p.n_cols);
-        uint32_t first = 1;
-        for (int s = 0; s < p.nslab; ++s) {
-          for (int dxi = 0; dxi < p.ndx; ++dxi) {
-            mbar_wait(bar_patch_full + 8 * ps, pph);
+    // ================================ MMA issuer (warp-uniform loops, one elected lane issues) ==
+    int ps = 0, bs = 0;
+    uint32_t pph = 0, bph = 0;
+    int it = 0;
+    const uint64_t desc_hi = umma_desc(0);     // descriptor with a zero start address
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const Tile tl = decode_tile(p, t, TILE_H);
+      const int outer_col = p.job[tl.job].outer_col;
+      const int buf = it % p.nbuf;
+      const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
+      mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + (uint32_t)(buf * NACC * p.n_cols);
+      uint32_t acc0 = 0;                        // 0 only for the very first MMA group of the tile
+      for (int s = 0; s < p.nslab; ++s) {
+        for (int dxi = 0; dxi < p.ndx; ++dxi) {
+          mbar_wait(bar_patch_full + 8 * ps, pph);
+          const uint32_t patch = s_patch + ps * Cfg::kPatchBytes;
+          for (int dyi = 0; dyi < p.ndy; ++dyi) {
+            mbar_wait(bar_b_full + 8 * bs, bph);
             tc_fence_after();
-            const uint32_t patch = s_patch + ps * Cfg::kPatchBytes;
-            for (int dyi = 0; dyi < p.ndy; ++dyi) {
-              mbar_wait(bar_b_full + 8 * bs, bph);
-              tc_fence_after();
-              const bool half = p.b_bytes[dxi][dyi] < (uint32_t)p.n_cols * 128u;
-              const uint32_t idesc = half ? p.idesc_half : p.idesc_full;
-              const uint32_t col = half ? (uint32_t)job.outer_col : 0u;
-              const uint64_t bdesc = umma_desc(s_b + bs * kBStageBytes);
+            const bool half = p.b_bytes[dxi][dyi] < (uint32_t)p.n_cols * 128u;
+            const uint32_t idesc = half ? p.idesc_half : p.idesc_full;
+            const uint32_t d0 = d_base + (half ? (uint32_t)outer_col : 0u);
+            const uint64_t bdesc = desc_hi | (uint64_t)(((s_b + bs * kBStageBytes) & 0x3FFFFu) >> 4);
+            const uint64_t adesc0 = desc_hi | (uint64_t)(((patch + (uint32_t)p.dy_ord[dyi] * ROW_BYTES) & 0x3FFFFu) >> 4);
+            if (elect_one()) {
+              if (!(p.debug & 8)) {
 #pragma unroll
-              for (int j = 0; j < NACC; ++j) {
-                const uint64_t adesc = umma_desc(patch + (uint32_t)(j * kTcRowsPerAcc + p.dy_ord[dyi]) * ROW_BYTES);
-                const uint32_t d = d_base + (uint32_t)(j * p.n_cols) + col;
+                for (int j = 0; j < NACC; ++j) {
+                  // accumulator j = image rows [8j, 8j+8) of the tile: +8 patch rows = +16 KB = +1024 (16-B units)
+                  const uint64_t adesc = adesc0 + (uint64_t)(j * kTcRowsPerAcc * (ROW_BYTES >> 4));
+                  const uint32_t d = d0 + (uint32_t)(j * p.n_cols);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t acc = (first && k == 0) ? 0u : 1u;
-                  // +32 B per K step inside the 128-B swizzled row == +2 in the 16-B address field
-                  if (p.is_tf32) umma_tf32(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-                  else           umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                  for (int k = 0; k < 4; ++k) {
+                    // +32 B per K step inside the 128-B swizzled row == +2 in the 16-B address field
+                    if (OPERAND == TC_TF32) umma_tf32(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? acc0 : 1u);
+                    else                    umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? acc0 : 1u);
+                  }
                 }
               }
-              first = 0;
               umma_commit(bar_b_empty + 8 * bs);
-              if (++bs == kBStages) { bs = 0; bph ^= 1; }
+              if (dyi == p.ndy - 1) umma_commit(bar_patch_empty + 8 * ps);
+              if (dyi == p.ndy - 1 && dxi == p.ndx - 1 && s == p.nslab - 1) umma_commit(bar_acc_full + 8 * buf);
             }
-            umma_commit(bar_patch_empty + 8 * ps);
-            if (++ps == NPB) { ps = 0; pph ^= 1; }
+            __syncwarp();
+            acc0 = 1;
+            if (++bs == kBStages) { bs = 0; bph ^= 1; }
           }
+          if (++ps == NPB) { ps = 0; pph ^= 1; }
         }
-        umma_commit(bar_acc_full + 8 * buf);
       }
     }
-    __syncwarp();
   } else {
     // ================================ epilogue =================================================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
@@ -332,11 +364,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r);
           tmem_ld_wait();
-          if (valid) {
-            if (p.out_act == ACT_F32) store_chunk<float>(r, job, pix, c0, p.relu != 0, p.is_tf32 != 0);
-            else if (p.out_act == ACT_BF16) store_chunk<__nv_bfloat16>(r, job, pix, c0, p.relu != 0);
-            else store_chunk<__half>(r, job, pix, c0, p.relu != 0);
-          }
+          if (valid && !(p.debug & 1)) store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32);
         }
       }
       tc_fence_before();
@@ -513,13 +541,13 @@ cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, i
 }
 
 namespace {
-template <int NACC>
+template <int NACC, int OPERAND>
 cudaError_t launch_nacc(const CUtensorMap& tmap, TcKParams& kp, cudaStream_t st) {
   using Cfg = TcCfg<NACC>;
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<NACC, OPERAND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     int dev = 0;
@@ -534,7 +562,7 @@ cudaError_t launch_nacc(const CUtensorMap& tmap, TcKParams& kp, cudaStream_t st)
   kp.nbuf = (2 * NACC * kp.n_cols <= 512) ? 2 : 1;
   kp.patch_tx = (uint32_t)(tile_h + kp.ks - 1) * kTcTileW * 128u;
   const int grid = kp.total_tiles < num_sms ? kp.total_tiles : num_sms;
-  conv_tc_kernel<NACC><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmap, kp);
+  conv_tc_kernel<NACC, OPERAND><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmap, kp);
   return cudaGetLastError();
 }
 }  // namespace
@@ -555,12 +583,27 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const TcConvPlan& plan, cons
   kp.idesc_full = make_idesc(plan.operand, plan.n_cols);
   kp.idesc_half = make_idesc(plan.operand, 64);
   kp.relu = L.relu; kp.out_act = L.out_act; kp.is_tf32 = plan.operand == TC_TF32;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("CODON_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    kp.debug = dbg;
+  }
+  if (L.out_act != (plan.operand == TC_TF32 ? ACT_F32 : plan.operand == TC_BF16 ? ACT_BF16 : ACT_F16))
+    return cudaErrorInvalidValue;   // activations are stored in the operand type
+#define CODON_TC_DISPATCH(N)                                                   \
+  switch (plan.operand) {                                                      \
+    case TC_F16: return launch_nacc<N, TC_F16>(tmap, kp, st);                  \
+    case TC_BF16: return launch_nacc<N, TC_BF16>(tmap, kp, st);                \
+    case TC_TF32: return launch_nacc<N, TC_TF32>(tmap, kp, st);                \
+    default: return cudaErrorInvalidValue;                                     \
+  }
   switch (L.nacc) {
-    case 1: return launch_nacc<1>(tmap, kp, st);
-    case 2: return launch_nacc<2>(tmap, kp, st);
-    case 4: return launch_nacc<4>(tmap, kp, st);
+    case 1: CODON_TC_DISPATCH(1)
+    case 2: CODON_TC_DISPATCH(2)
+    case 4: CODON_TC_DISPATCH(4)
     default: return cudaErrorInvalidValue;
   }
+#undef CODON_TC_DISPATCH
 }
 
 }  // namespace codon
