@@ -88,32 +88,45 @@ __global__ void __launch_bounds__(256) cac_stats_kernel(const T* __restrict__ F,
   }
 }
 
-// One CTA per frame, 128 threads.  F channel c (depth 0..63 | colour 64..127) is Fcat channel
+// One CTA per frame, 1024 threads.  F channel c (depth 0..63 | colour 64..127) is Fcat channel
 // (c + 64) % 128 (Fcat = [colour | depth], CODON_x4.py:85); w1 is indexed by Fcat channel.
-__global__ void __launch_bounds__(128) cac_mlp_kernel(const float* __restrict__ part, int chunks, int HW,
-                                                      const float* __restrict__ w1,
-                                                      const float* __restrict__ b1,
-                                                      const float* __restrict__ w2,
-                                                      const float* __restrict__ b2,
-                                                      float* __restrict__ sc) {
-  __shared__ float avg[128], mx[128], hid[2][8];
-  const int b = blockIdx.x, t = threadIdx.x;
-  float s = 0.f, m = -INFINITY;
+// The chunk partials are reduced in a fixed order (4 interleaved lanes per column, then a fixed
+// 4-way combine), so the result does not depend on the batch size or the GPU count.
+__global__ void __launch_bounds__(1024) cac_mlp_kernel(const float* __restrict__ part, int chunks, int HW,
+                                                       const float* __restrict__ w1,
+                                                       const float* __restrict__ b1,
+                                                       const float* __restrict__ w2,
+                                                       const float* __restrict__ b2,
+                                                       float* __restrict__ sc) {
+  __shared__ float red[4][256], avg[128], mx[128], hid[2][8];
+  const int b = blockIdx.x, t = threadIdx.x, col = t & 255, grp = t >> 8;
   const float* src = part + (size_t)b * chunks * 256;
-  for (int c = 0; c < chunks; ++c) {
-    s += src[(size_t)c * 256 + t];
-    m = fmaxf(m, src[(size_t)c * 256 + 128 + t]);
+  const bool is_max = col >= 128;
+  float acc = is_max ? -INFINITY : 0.f;
+  for (int c = grp; c < chunks; c += 4) {
+    const float v = src[(size_t)c * 256 + col];
+    acc = is_max ? fmaxf(acc, v) : acc + v;
   }
-  const int fc = (t + 64) & 127;
-  avg[fc] = s / (float)HW;
-  mx[fc] = m;
+  red[grp][col] = acc;
   __syncthreads();
-  if (t < 16) {
-    const int h = t & 7;
-    const float* v = (t < 8) ? avg : mx;
-    float a = b1[h];
-    for (int j = 0; j < 128; ++j) a = fmaf(w1[h * 128 + j], v[j], a);
-    hid[t >> 3][h] = fmaxf(a, 0.f);
+  if (t < 256) {
+    float r = red[0][t];
+#pragma unroll
+    for (int g = 1; g < 4; ++g) r = is_max ? fmaxf(r, red[g][t]) : r + red[g][t];
+    const int fc = ((t & 127) + 64) & 127;
+    if (is_max) mx[fc] = r; else avg[fc] = r / (float)HW;
+  }
+  __syncthreads();
+  if (t < 512) {
+    // 16 hidden units x 32 lanes: warp w computes hidden unit (w & 7) of the avg (w < 8) or max branch
+    const int w = t >> 5, lane = t & 31, h = w & 7;
+    const float* v = (w < 8) ? avg : mx;
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a = fmaf(w1[h * 128 + lane * 4 + j], v[lane * 4 + j], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) hid[w >> 3][h] = fmaxf(a + b1[h], 0.f);
   }
   __syncthreads();
   if (t < 64) {
@@ -203,7 +216,7 @@ cudaError_t launch_cac_stats(const void* F, int act, int B, int H, int W, float*
 
 cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const float* w1, const float* b1,
                            const float* w2, const float* b2, float* sc, cudaStream_t st) {
-  cac_mlp_kernel<<<B, 128, 0, st>>>(part, chunks, HW, w1, b1, w2, b2, sc);
+  cac_mlp_kernel<<<B, 1024, 0, st>>>(part, chunks, HW, w1, b1, w2, b2, sc);
   return cudaGetLastError();
 }
 

@@ -41,6 +41,7 @@ constexpr int kThreads = 192;
 struct TcKParams {
   TcJob job[2];
   int njobs, B, H, W, tiles_x, tiles_y, tiles_per_job, total_tiles;
+  int main_tiles, total_items;   // items [0, main_tiles) are full tiles; the tail tiles are split into single sub-tiles
   int nslab, slab_elems, ks, pad, ndx, ndy;
   int dx_ord[kTcMaxTaps], dy_ord[kTcMaxTaps];
   uint32_t b_bytes[kTcMaxTaps][kTcMaxTaps], b_off[kTcMaxTaps][kTcMaxTaps];
@@ -165,15 +166,26 @@ template <> struct OperandTraits<TC_F16> { using Out = __half; };
 template <> struct OperandTraits<TC_BF16> { using Out = __nv_bfloat16; };
 template <> struct OperandTraits<TC_TF32> { using Out = float; };
 
-struct Tile { int job, n, y0, x0; };
-__device__ __forceinline__ Tile decode_tile(const TcKParams& p, int t, int tile_h) {
+struct Tile { int job, n, y0, x0, nacc; };
+// Work item -> tile.  Full tiles hold NACC vertically adjacent 128-pixel sub-tiles.  The tiles of the
+// last, partial wave (total_tiles % gridDim of them) are handed out as NACC separate single
+// sub-tile items instead, so the tail of the launch costs ~1/NACC of a wave.
+__device__ __forceinline__ Tile decode_tile(const TcKParams& p, int item, int nacc_full) {
   Tile r;
+  int t = item, sub = 0;
+  r.nacc = nacc_full;
+  if (item >= p.main_tiles) {
+    const int k = item - p.main_tiles;
+    t = p.main_tiles + k / nacc_full;
+    sub = k - (k / nacc_full) * nacc_full;
+    r.nacc = 1;
+  }
   r.job = t / p.tiles_per_job;
   int q = t - r.job * p.tiles_per_job;
   const int per_frame = p.tiles_x * p.tiles_y;
   r.n = q / per_frame;
   q -= r.n * per_frame;
-  r.y0 = (q / p.tiles_x) * tile_h;
+  r.y0 = (q / p.tiles_x) * (nacc_full * kTcRowsPerAcc) + sub * kTcRowsPerAcc;
   r.x0 = (q % p.tiles_x) * kTcTileW;
   return r;
 }
@@ -252,8 +264,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     // ================================ producer (warp-uniform loops, one elected lane issues) ====
     int ps = 0, bs = 0;
     uint32_t pph = 0, bph = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const Tile tl = decode_tile(p, t, TILE_H);
+    for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
+      const Tile tl = decode_tile(p, t, NACC);
+      if (tl.y0 >= p.H) continue;                 // empty sub-tile of a split tail tile
       const TcJob& job = p.job[tl.job];
       for (int s = 0; s < p.nslab; ++s) {
         const uint8_t* wslab = job.w + (size_t)s * p.slab_bytes;
@@ -291,8 +304,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     uint32_t pph = 0, bph = 0;
     int it = 0;
     const uint64_t desc_hi = umma_desc(0);     // descriptor with a zero start address
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const Tile tl = decode_tile(p, t, TILE_H);
+    for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
+      const Tile tl = decode_tile(p, t, NACC);
+      if (tl.y0 >= p.H) continue;
       const int outer_col = p.job[tl.job].outer_col;
       const int buf = it % p.nbuf;
       const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
@@ -302,10 +316,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       uint32_t acc0 = 0;                        // 0 only for the very first MMA group of the tile
       for (int s = 0; s < p.nslab; ++s) {
         for (int dxi = 0; dxi < p.ndx; ++dxi) {
-          mbar_wait(bar_patch_full + 8 * ps, pph);
+          if (!(p.debug & 16)) mbar_wait(bar_patch_full + 8 * ps, pph);
           const uint32_t patch = s_patch + ps * Cfg::kPatchBytes;
           for (int dyi = 0; dyi < p.ndy; ++dyi) {
-            mbar_wait(bar_b_full + 8 * bs, bph);
+            if (!(p.debug & 16)) mbar_wait(bar_b_full + 8 * bs, bph);
             tc_fence_after();
             const bool half = p.b_bytes[dxi][dyi] < (uint32_t)p.n_cols * 128u;
             const uint32_t idesc = half ? p.idesc_half : p.idesc_full;
@@ -316,6 +330,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               if (!(p.debug & 8)) {
 #pragma unroll
                 for (int j = 0; j < NACC; ++j) {
+                  if (j >= tl.nacc) break;
                   // accumulator j = image rows [8j, 8j+8) of the tile: +8 patch rows = +16 KB = +1024 (16-B units)
                   const uint64_t adesc = adesc0 + (uint64_t)(j * kTcRowsPerAcc * (ROW_BYTES >> 4));
                   const uint32_t d = d0 + (uint32_t)(j * p.n_cols);
@@ -338,6 +353,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           if (++ps == NPB) { ps = 0; pph ^= 1; }
         }
       }
+      ++it;
     }
   } else {
     // ================================ epilogue =================================================
@@ -345,30 +361,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int m = q * 32 + lane;                 // accumulator row == pixel inside the sub-tile
     const int my = m / kTcTileW, mx = m % kTcTileW;
     int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const Tile tl = decode_tile(p, t, TILE_H);
+    for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
+      const Tile tl = decode_tile(p, t, NACC);
+      if (tl.y0 >= p.H) continue;
       const TcJob& job = p.job[tl.job];
       const int buf = it % p.nbuf;
       const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
       mbar_wait(bar_acc_full + 8 * buf, aph);
       tc_fence_after();
       const int px = tl.x0 + mx;
-#pragma unroll 1
-      for (int j = 0; j < NACC; ++j) {
+      // software-pipelined drain: the TMEM load of chunk i+1 is in flight while chunk i is converted
+      // and stored (chunk = 32 accumulator columns of one 128-pixel sub-tile)
+      const int cpa = p.n_cols >> 5, nchunk = tl.nacc * cpa;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NACC * p.n_cols);
+      auto issue = [&](int i, uint32_t (&r)[32]) { tmem_ld32(lane_base + (uint32_t)(i << 5), r); };
+      auto drain = [&](int i, const uint32_t (&r)[32]) {
+        const int j = i / cpa, c0 = (i - j * cpa) << 5;
         const int py = tl.y0 + j * kTcRowsPerAcc + my;
-        const bool valid = (py < p.H) && (px < p.W);
-        const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
-        const uint32_t tcol = (uint32_t)(buf * NACC * p.n_cols + j * p.n_cols);
-#pragma unroll 1
-        for (int c0 = 0; c0 < p.n_cols; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r);
-          tmem_ld_wait();
-          if (valid && !(p.debug & 1)) store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32);
+        if ((py < p.H) && (px < p.W) && !(p.debug & 1)) {
+          const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
+          store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32);
         }
+      };
+      uint32_t ra[32], rb[32];
+      issue(0, ra);
+#pragma unroll 1
+      for (int i = 0; i < nchunk; i += 2) {
+        tmem_ld_wait();
+        issue(i + 1, rb);
+        drain(i, ra);
+        tmem_ld_wait();
+        if (i + 2 < nchunk) issue(i + 2, ra);
+        drain(i + 1, rb);
       }
       tc_fence_before();
       mbar_arrive(bar_acc_empty + 8 * buf);
+      ++it;
     }
   }
 
@@ -559,6 +587,14 @@ cudaError_t launch_nacc(const CUtensorMap& tmap, TcKParams& kp, cudaStream_t st)
   kp.tiles_y = cdiv(kp.H, tile_h);
   kp.tiles_per_job = kp.B * kp.tiles_x * kp.tiles_y;
   kp.total_tiles = kp.tiles_per_job * kp.njobs;
+  {
+    const int g = kp.total_tiles < num_sms ? kp.total_tiles : num_sms;
+    const int rem = kp.total_tiles % g;
+    // split the tail only when that shortens it: rem*NACC single sub-tiles over g CTAs
+    const bool split = NACC > 1 && kp.total_tiles > g && cdiv(rem * NACC, g) < NACC;
+    kp.main_tiles = split ? kp.total_tiles - rem : kp.total_tiles;
+    kp.total_items = kp.main_tiles + (kp.total_tiles - kp.main_tiles) * NACC;
+  }
   kp.nbuf = (2 * NACC * kp.n_cols <= 512) ? 2 : 1;
   kp.patch_tx = (uint32_t)(tile_h + kp.ks - 1) * kTcTileW * 128u;
   const int grid = kp.total_tiles < num_sms ? kp.total_tiles : num_sms;

@@ -1,0 +1,112 @@
+"""Frame / tile scheduling across the GPUs of one box.
+
+Two levels:
+
+* **Inside a GPU** the spatial tiling is done by the kernels themselves: every convolution launch
+  walks a persistent tile list (16 x 8*NACC output pixels per tile), each tile's input is a
+  halo-overlapped patch (tile + (k-1) rows/columns) fetched by TMA with hardware zero fill at the
+  image border, and the per-stage CAC statistics are reduced over fixed 1024-pixel chunks in a fixed
+  order.  This is design (A) of SURVEY.md 5.7 ("stage-synchronous tiling") at layer granularity, so
+  the result is independent of the tile size and exact for any frame size -- a 1920x1080 frame is
+  ~4050 tiles per launch.  No host-side stitching is needed.
+* **Across GPUs** whole frames are sharded: frames are independent (CAC pools per sample), so there
+  is no collective on the compute path.  The only communication is one all-reduce of
+  ``[rmse_sum, ssim_sum, count]`` (float64) at the end (replaces the running sums of
+  CODON_X4/test.py:140-145), NCCL over NVLink when launched one process per GPU, or nothing at all
+  in the single-process multi-thread mode.
+
+This module holds the host-side part: the deterministic frame -> rank/GPU assignment, batching of
+same-shaped frames under a memory budget, a thread-per-GPU executor for single-process use, and the
+metric reduction.
+"""
+from __future__ import annotations
+
+import threading
+from collections import defaultdict
+from dataclasses import dataclass
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+
+
+def shard_indices(n_items: int, world: int, rank: int) -> List[int]:
+    """Round-robin assignment (item i -> rank i mod world): balanced for any n, deterministic, and
+    independent of the order in which ranks run."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad world/rank {world}/{rank}")
+    return list(range(rank, n_items, world))
+
+
+@dataclass
+class Batch:
+    indices: List[int]          # positions in the caller's frame list
+    shape: Tuple[int, int]      # (H, W)
+
+
+def plan_batches(shapes: Sequence[Tuple[int, int]], indices: Iterable[int], max_pixels: int) -> List[Batch]:
+    """Groups frames of identical (H, W) into batches of at most ``max_pixels`` pixels per launch
+    (one C-ABI call per batch amortises launch overhead and fills the last tile wave).  Order inside
+    a shape group follows ``indices``; a frame larger than ``max_pixels`` still gets its own batch."""
+    groups: Dict[Tuple[int, int], List[int]] = defaultdict(list)
+    order: List[Tuple[int, int]] = []
+    for i in indices:
+        s = tuple(shapes[i])
+        if s not in groups:
+            order.append(s)
+        groups[s].append(i)
+    out: List[Batch] = []
+    for s in order:
+        per = max(1, max_pixels // (s[0] * s[1]))
+        g = groups[s]
+        for k in range(0, len(g), per):
+            out.append(Batch(g[k:k + per], s))
+    return out
+
+
+def max_pixels_for_budget(workspace_bytes_per_pixel: float, budget_bytes: int) -> int:
+    return max(1, int(budget_bytes // max(1.0, workspace_bytes_per_pixel)))
+
+
+def reduce_metric_sums(rmse_sum: float, ssim_sum: float, count: int,
+                       device: Optional[torch.device] = None) -> Tuple[float, float, int]:
+    """All-reduce (SUM) of the three float64 running sums over the process group, if there is one."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return rmse_sum, ssim_sum, count
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([rmse_sum, ssim_sum, float(count)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t[0]), float(t[1]), int(round(float(t[2])))
+
+
+class MultiGpuExecutor:
+    """Single-process executor: one host thread and one engine per GPU.  ctypes releases the GIL for
+    the duration of each C-ABI call, so the per-GPU threads overlap.  ``fn(gpu_index, item)`` is run
+    for every item on the GPU that owns it; results come back in item order."""
+
+    def __init__(self, gpu_ids: Sequence[int]):
+        if not gpu_ids:
+            raise ValueError("no GPUs given")
+        self.gpu_ids = list(gpu_ids)
+
+    def map(self, fn: Callable[[int, object], object], items: Sequence[object]) -> List[object]:
+        results: List[object] = [None] * len(items)
+        errors: List[BaseException] = []
+
+        def worker(slot: int, gpu: int):
+            try:
+                torch.cuda.set_device(gpu)
+                for i in shard_indices(len(items), len(self.gpu_ids), slot):
+                    results[i] = fn(gpu, items[i])
+            except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(s, g), daemon=True) for s, g in enumerate(self.gpu_ids)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results

@@ -1,0 +1,97 @@
+"""GPU: the test.py-compatible driver on the bundled Middlebury images (tests/golden/images), and
+RMSE/SSIM parity of the reduced-precision modes against the reference fp32 forward (north_star:
+"RMSE/SSIM identical to 3 decimals ... in bf16 mode").
+
+The reference's own result for Tsukuba (fp32 CPU forward of the real reference class with synthetic
+weights seed 0) is committed as tests/golden/fwd_x4_s0_tsukuba.npz.  SURVEY.md 7.3(4) measured that
+truncation to uint8 makes 3-decimal RMSE equality unreachable for bf16 operands; the achieved
+deltas are printed and bounded here instead of being assumed.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import codon_oracle as orc
+from codon_b200 import engine, test as driver
+from codon_b200.CODON_x4 import CODONNet
+
+pytestmark = pytest.mark.gpu
+
+
+def _imread(p):
+    import cv2
+    return cv2.imread(p, 0)
+
+
+def _metrics_cpu(out_f32, label_u8):
+    q = orc.quantise_output(out_f32)
+    return orc.masked_rmse(label_u8, q), orc.ssim_gauss(label_u8 / 255, q / 255), q
+
+
+def test_tsukuba_modes_vs_reference_fp32(golden_dir):
+    g = np.load(os.path.join(golden_dir, "fwd_x4_s0_tsukuba.npz"))
+    img = os.path.join(golden_dir, "images")
+    d = _imread(os.path.join(img, "depth_x4", "Tsukuba.png"))
+    c = _imread(os.path.join(img, "gray", "Tsukuba.png"))
+    lab = _imread(os.path.join(img, "label", "Tsukuba.png"))
+    ref = g["out_fp32"][0, 0]
+    r_ref, s_ref, q_ref = _metrics_cpu(ref, lab)
+    x = torch.from_numpy(d / 255).float()[None, None].cuda()
+    y = torch.from_numpy(c / 255).float()[None, None].cuda()
+    sd = orc.synthetic_state_dict(4, 0)
+    report = {}
+    for mode in ("fp32", "tf32", "fp16", "bf16"):
+        net = CODONNet().eval().set_mode(mode)
+        net.load_state_dict(sd)
+        with torch.no_grad():
+            out = net(x, y)
+        err = float(np.abs(out.cpu().numpy()[0, 0] - ref).max())
+        q = engine.quantise_u8(out[0, 0])
+        r = float(engine.masked_rmse(torch.from_numpy(lab).cuda()[None], q[None])[0])
+        s = float(engine.ssim_gauss(torch.from_numpy(lab).cuda()[None], q[None])[0])
+        flipped = float((q.cpu().numpy() != q_ref).mean())
+        report[mode] = dict(max_abs=err, rmse=r, ssim=s, d_rmse=r - r_ref, d_ssim=s - s_ref, px_changed=flipped)
+    print(json.dumps({"reference_fp32": dict(rmse=r_ref, ssim=s_ref), **report}, indent=1))
+    assert report["fp32"]["max_abs"] <= 1e-4 and report["tf32"]["max_abs"] <= 1e-3 and report["fp16"]["max_abs"] <= 1e-3
+    assert round(report["fp32"]["rmse"], 3) == round(r_ref, 3) and round(report["fp32"]["ssim"], 3) == round(s_ref, 3)
+    for mode, (dr, ds) in {"tf32": (5e-3, 5e-4), "fp16": (5e-3, 5e-4), "bf16": (5e-2, 1e-3)}.items():
+        assert abs(report[mode]["d_rmse"]) <= dr, (mode, report[mode])
+        assert abs(report[mode]["d_ssim"]) <= ds, (mode, report[mode])
+
+
+def test_driver_end_to_end_on_bundled_images(golden_dir, tmp_path, capsys):
+    """codon_b200.test.main with the reference's flags + data-path flags; checks the printed
+    per-image lines and means against the CPU oracle metrics of the written PNGs."""
+    img = os.path.join(golden_dir, "images")
+    out_dir = tmp_path / "CODON_result_save"
+    res = driver.main(["--gpus", "0", "--scale", "4", "--mode", "fp16", "--input-depth", os.path.join(img, "depth_x4"),
+                       "--input-color", os.path.join(img, "gray"), "--label", os.path.join(img, "label"),
+                       "--out", str(out_dir) + "/", "--log", str(tmp_path / "log.txt"), "--seed", "1"])
+    import sys
+    sys.stdout = sys.__stdout__
+    mean_rmse, mean_ssim, n = res
+    assert n == 10
+    names = sorted(os.listdir(os.path.join(img, "gray")))
+    rm, ss = [], []
+    for nme in names:
+        out = _imread(str(out_dir / nme))
+        lab = _imread(os.path.join(img, "label", nme))
+        assert out is not None and out.shape == lab.shape
+        rm.append(orc.masked_rmse(lab, out))
+        ss.append(orc.ssim_gauss(lab / 255, out / 255))
+    assert abs(np.mean(rm) - mean_rmse) < 1e-9 and abs(np.mean(ss) - mean_ssim) < 1e-9
+    log = open(tmp_path / "log.txt").read()
+    assert "Tsukuba.png" in log and log.strip().splitlines()[-2] == "10"
+
+
+def test_evaluationresults_and_ssim_exact_dropins(golden_dir):
+    metrics = json.load(open(os.path.join(golden_dir, "metrics.json")))
+    img = os.path.join(golden_dir, "images")
+    lab = _imread(os.path.join(img, "label", "Art.png"))
+    out = _imread(os.path.join(img, "ref_out_x8", "Art.png"))
+    from codon_b200.ssim_2 import ssim_exact
+    assert abs(driver.EvaluationResults(lab, out) - metrics["x8/Art.png"]["rmse_out"]) < 1e-12
+    assert abs(ssim_exact(lab / 255, out / 255) - metrics["x8/Art.png"]["ssim_out"]) < 1e-10
