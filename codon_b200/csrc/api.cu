@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -206,7 +207,11 @@ int get_tmap(codon_ctx* ctx, const void* base, int C, int box_rows, int slab_ele
   return CODON_OK;
 }
 
-int pick_nacc(int B, int H, int W, int njobs) {
+int pick_nacc(int B, int H, int W, int njobs, const char* env = nullptr) {
+  if (env) {                      // perf experiments: CODON_TC_NACC_PAIR / CODON_TC_NACC_CONV
+    const char* e = getenv(env);
+    if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) return atoi(e);
+  }
   const int tx = cdiv(W, kTcTileW);
   for (int nacc : {4, 2}) {
     const long tiles = (long)B * tx * cdiv(H, nacc * kTcRowsPerAcc) * njobs;
@@ -242,7 +247,7 @@ struct Runner {
     const TcLayer& l0 = ctx->w_tc.at(jobs[0].w);
     TcLaunch L;
     L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = relu; L.out_act = ctx->act;
-    L.nacc = pick_nacc(B, H, W, njobs);
+    L.nacc = pick_nacc(B, H, W, njobs, "CODON_TC_NACC_CONV");
     for (int i = 0; i < njobs; ++i) {
       const TcLayer& l = ctx->w_tc.at(jobs[i].w);
       L.job[i].in_coff = jobs[i].in_off;
@@ -286,7 +291,7 @@ struct Runner {
     const TcLayer& l0 = ctx->w_tc.at(wpair[0]);
     TcLaunch L;
     L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = 1; L.out_act = ctx->act;
-    L.nacc = pick_nacc(B, H, W, njobs);
+    L.nacc = pick_nacc(B, H, W, njobs, "CODON_TC_NACC_PAIR");
     for (int i = 0; i < njobs; ++i) {
       const TcLayer& l = ctx->w_tc.at(wpair[i]);
       L.job[i].in_coff = in_off[i];
