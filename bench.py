@@ -286,6 +286,10 @@ def run_gpu(a):
         "achieved": tfs, "peak": peak_tf, "unit": "TFLOP/s", "frac": tfs / peak_tf, "traffic": None,
         "peak_source": peaks["source"] + ", dense bf16 burst" +
                        ("; tf32 runs at half the bf16 rate, so frac <= 0.5 in this mode" if a.mode == "tf32" else ""),
+        "peak_for_this_dtype": peak_tf / 2 if a.mode == "tf32" else peak_tf,
+        "frac_of_dtype_peak": tfs / (peak_tf / 2 if a.mode == "tf32" else peak_tf),
+        "frac_of_sustained_peak": (tfs / peaks["bf16_tflops_sustained"] / (0.5 if a.mode == "tf32" else 1.0))
+                                  if peaks.get("bf16_tflops_sustained") else None,
         "flop_per_launch": dom["work"] / max(1, dom["launches"]), "ms_per_launch": dom["ms"] / max(1, dom["launches"]),
         "launches": dom["launches"], "share_of_step": dom["ms"] / all_ms if all_ms else None,
         "trunk_all_convs": {"achieved": syn.FLOPS_PER_PIXEL * P * steps / (conv_ms / 1e3) / 1e12 if conv_ms else None,

@@ -51,6 +51,7 @@ const ConvSpec kTrunk[] = {
 struct TcLayer {
   TcConvPlan plan;
   uint8_t* dev = nullptr;
+  CUtensorMap bmap;            // 2-D view of the packed stream (2-CTA kernel)
 };
 
 struct Buffers {
@@ -207,17 +208,30 @@ int get_tmap(codon_ctx* ctx, const void* base, int C, int box_rows, int slab_ele
   return CODON_OK;
 }
 
-int pick_nacc(int B, int H, int W, int njobs, const char* env = nullptr) {
+// Accumulators (128-pixel sub-tiles) per CTA tile.  `prefer` is the size that measured fastest for the
+// layer class when the frame is large enough: 2 for the 5x5 layers in cluster mode (two TMEM buffers of
+// 2 accumulators -> the epilogue of a tile overlaps the MMAs of the next one), 4 for the HBM-bound
+// 1x1 / 3x3 layers (fewer, larger TMA boxes).  Small frames step down until there are >= 2 waves.
+int pick_nacc(int B, int H, int W, int njobs, int prefer, const char* env = nullptr) {
   if (env) {                      // perf experiments: CODON_TC_NACC_PAIR / CODON_TC_NACC_CONV
     const char* e = getenv(env);
     if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) return atoi(e);
   }
   const int tx = cdiv(W, kTcTileW);
-  for (int nacc : {4, 2}) {
+  for (int nacc = prefer; nacc > 1; nacc >>= 1) {
     const long tiles = (long)B * tx * cdiv(H, nacc * kTcRowsPerAcc) * njobs;
     if (tiles >= 2 * 148) return nacc;
   }
   return 1;
+}
+
+// The cluster-of-2 kernel pays off once a job has at least a couple of waves of tile pairs.
+int use_two_cta(int B, int H, int W, int nacc) {
+  static int env = -2;
+  if (env == -2) { const char* e = getenv("CODON_TC_2CTA"); env = e ? atoi(e) : -1; }
+  if (env == 0 || env == 1) return env;
+  const long tiles = (long)B * cdiv(W, kTcTileW) * cdiv(H, nacc * kTcRowsPerAcc);
+  return tiles >= 148 ? 1 : 0;
 }
 
 // One conv layer of the plan: up to two jobs reading channel slices of `in` (in_C channels).
@@ -247,7 +261,7 @@ struct Runner {
     const TcLayer& l0 = ctx->w_tc.at(jobs[0].w);
     TcLaunch L;
     L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = relu; L.out_act = ctx->act;
-    L.nacc = pick_nacc(B, H, W, njobs, "CODON_TC_NACC_CONV");
+    L.nacc = pick_nacc(B, H, W, njobs, ks == 5 ? 2 : 4, "CODON_TC_NACC_CONV");
     for (int i = 0; i < njobs; ++i) {
       const TcLayer& l = ctx->w_tc.at(jobs[i].w);
       L.job[i].in_coff = jobs[i].in_off;
@@ -256,7 +270,10 @@ struct Runner {
       L.job[i].res = jobs[i].has_res ? ws + jobs[i].res : nullptr;
       L.job[i].res_stride = jobs[i].res_stride; L.job[i].res_off = jobs[i].res_off;
       L.job[i].outer_col = 0;
+      L.bmap[i] = &l.bmap;
     }
+    // the HBM-bound 1x1 / 3x3 layers measured slower in cluster mode; the 5x5 layers gain 15-20 %
+    L.two_cta = ks == 5 ? use_two_cta(B, H, W, L.nacc) : 0;
     const CUtensorMap* tm = nullptr;
     int rc = get_tmap(ctx, ws + in, in_C, tc_box_rows(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
     if (rc) return rc;
@@ -291,7 +308,7 @@ struct Runner {
     const TcLayer& l0 = ctx->w_tc.at(wpair[0]);
     TcLaunch L;
     L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = 1; L.out_act = ctx->act;
-    L.nacc = pick_nacc(B, H, W, njobs, "CODON_TC_NACC_PAIR");
+    L.nacc = pick_nacc(B, H, W, njobs, 2, "CODON_TC_NACC_PAIR");
     for (int i = 0; i < njobs; ++i) {
       const TcLayer& l = ctx->w_tc.at(wpair[i]);
       L.job[i].in_coff = in_off[i];
@@ -299,7 +316,9 @@ struct Runner {
       L.job[i].out = ws + out; L.job[i].out_stride = out_stride; L.job[i].out_off = out_off[i];
       L.job[i].res = nullptr; L.job[i].res_stride = 0; L.job[i].res_off = 0;
       L.job[i].outer_col = three_first[i] ? 64 : 0;
+      L.bmap[i] = &l.bmap;
     }
+    L.two_cta = use_two_cta(B, H, W, L.nacc);
     const CUtensorMap* tm = nullptr;
     int rc = get_tmap(ctx, ws + in, in_C, tc_box_rows(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
     if (rc) return rc;
@@ -539,6 +558,7 @@ int codon_finalize_weights(codon_ctx* ctx) {
       l.plan = tc_make_plan(s.ks, s.cin, s.cout, operand);
       tc_pack_weights(l.plan, W(s.name).data.data(), packed);
       if ((rc = upload(ctx, packed, &l.dev))) return rc;
+      CU_TRY(ctx, tc_encode_bmap(&l.bmap, l.dev, packed.size()));
       ctx->w_tc[s.name] = l;
     }
     struct PairSpec { const char* name; const char* w3; const char* w5; bool three_first; };
@@ -549,6 +569,7 @@ int codon_finalize_weights(codon_ctx* ctx) {
       l.plan = tc_make_pair_plan(64, operand);
       tc_pack_pair_weights(l.plan, W(p.w3).data.data(), W(p.w5).data.data(), p.three_first, packed);
       if ((rc = upload(ctx, packed, &l.dev))) return rc;
+      CU_TRY(ctx, tc_encode_bmap(&l.bmap, l.dev, packed.size()));
       ctx->w_tc[p.name] = l;
     }
   }

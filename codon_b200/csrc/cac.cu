@@ -19,13 +19,17 @@
 namespace codon {
 namespace {
 
-constexpr int kChunkPx = 1024;   // pixels per stats CTA; fixed so that results are batch-invariant
+constexpr int kChunkPx = 256;    // pixels per stats CTA; fixed so that results are batch-invariant
 
+// 256 threads; every thread keeps kU 16-byte loads in flight (memory-latency bound otherwise: the
+// r01 version had 4 loads per thread and 0.5 waves at B=1 and reached 1.5-2.4 TB/s).
 template <typename T>
-__global__ void __launch_bounds__(256) cac_stats_kernel(const T* __restrict__ F, int HW, int chunks,
+__global__ void __launch_bounds__(256, 4) cac_stats_kernel(const T* __restrict__ F, int HW, int chunks,
                                                         float* __restrict__ pooled,
                                                         float* __restrict__ part) {
-  constexpr int V = Act<T>::kVec, LPP = 128 / V, PPW = 32 / LPP, U = 4;
+  constexpr int V = Act<T>::kVec, LPP = 128 / V, PPW = 32 / LPP, kU = 8;
+  constexpr int ROWPX = 8 * PPW;                 // pixels covered by one load instruction of the CTA
+  constexpr int NIT = kChunkPx / (ROWPX * kU);   // 2 (16-bit) or 4 (fp32) batches of kU loads
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane % LPP, sub = lane / LPP;
   const int p_begin = chunk * kChunkPx, p_end = min(p_begin + kChunkPx, HW);
@@ -36,27 +40,29 @@ __global__ void __launch_bounds__(256) cac_stats_kernel(const T* __restrict__ F,
 #pragma unroll
   for (int j = 0; j < V; ++j) { csum[j] = 0.f; cmax[j] = -INFINITY; }
 
-  for (int p0 = p_begin + warp * PPW + sub; p0 < p_end + 8 * PPW * U; p0 += 8 * PPW * U) {
-    // p0 - sub is warp-uniform, so the loop trip count is warp-uniform (shuffles below are safe)
-    if (p0 - sub >= p_end) break;
-    float v[U][V];
-    bool ok[U];
+#pragma unroll 1
+  for (int it = 0; it < NIT; ++it) {
+    const int p0 = p_begin + it * ROWPX * kU + warp * PPW + sub;
+    uint4 raw[kU];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = p0 + u * 8 * PPW;
-      ok[u] = p < p_end;
-      if (ok[u]) Act<T>::load(base + (size_t)p * 128 + g * V, v[u]);
+    for (int u = 0; u < kU; ++u) {
+      const int p = p0 + u * ROWPX;
+      raw[u] = p < p_end ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * 128 + g * V)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
+    for (int u = 0; u < kU; ++u) {
+      const int p = p0 + u * ROWPX;
+      const bool ok = p < p_end;
+      float v[V];
+      Act<T>::unpack(raw[u], v);
       float s = 0.f, m = -INFINITY;
-      if (ok[u]) {
+      if (ok) {
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          csum[j] += v[u][j];
-          cmax[j] = fmaxf(cmax[j], v[u][j]);
-          s += v[u][j];
-          m = fmaxf(m, v[u][j]);
+          csum[j] += v[j];
+          cmax[j] = fmaxf(cmax[j], v[j]);
+          s += v[j];
+          m = fmaxf(m, v[j]);
         }
       }
 #pragma unroll
@@ -64,10 +70,7 @@ __global__ void __launch_bounds__(256) cac_stats_kernel(const T* __restrict__ F,
         s += __shfl_xor_sync(0xffffffffu, s, o);
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
       }
-      if (ok[u] && g == 0) {
-        const int p = p0 + u * 8 * PPW;
-        *reinterpret_cast<float2*>(pl + (size_t)p * 2) = make_float2(m, s * (1.0f / 128.0f));
-      }
+      if (ok && g == 0) *reinterpret_cast<float2*>(pl + (size_t)p * 2) = make_float2(m, s * (1.0f / 128.0f));
     }
   }
 
@@ -103,9 +106,15 @@ __global__ void __launch_bounds__(1024) cac_mlp_kernel(const float* __restrict__
   const float* src = part + (size_t)b * chunks * 256;
   const bool is_max = col >= 128;
   float acc = is_max ? -INFINITY : 0.f;
-  for (int c = grp; c < chunks; c += 4) {
-    const float v = src[(size_t)c * 256 + col];
-    acc = is_max ? fmaxf(acc, v) : acc + v;
+  for (int c0 = grp; c0 < chunks; c0 += 32) {        // 8 independent loads in flight, combined in a fixed order
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + 4 * u;
+      v[u] = c < chunks ? src[(size_t)c * 256 + col] : (is_max ? -INFINITY : 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = is_max ? fmaxf(acc, v[u]) : acc + v[u];
   }
   red[grp][col] = acc;
   __syncthreads();

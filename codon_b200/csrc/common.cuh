@@ -19,6 +19,9 @@ template <> struct Act<float> {
     float4 r = *reinterpret_cast<const float4*>(p);
     v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
   }
+  __device__ static inline void unpack(const uint4& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  }
   __device__ static inline void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -29,6 +32,14 @@ template <> struct Act<__nv_bfloat16> {
   static constexpr int kVec = 8;
   __device__ static inline void load(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static inline void unpack(const uint4& r, float (&v)[8]) {
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -52,6 +63,14 @@ template <> struct Act<__half> {
   static constexpr int kVec = 8;
   __device__ static inline void load(const __half* p, float (&v)[8]) {
     uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ static inline void unpack(const uint4& r, float (&v)[8]) {
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

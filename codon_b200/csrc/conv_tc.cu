@@ -408,14 +408,294 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   }
 }
 
+// ================================================================================================
+// 2-CTA variant: a cluster of two CTAs (one SM pair) computes two tiles with ONE stream of
+// tcgen05.mma.cta_group::2 instructions (M = 256: 128 pixels of each CTA's tile).  Each CTA stages its
+// own activation patch and only HALF of every weight block (N/2 rows), so the per-SM shared-memory
+// operand traffic per MMA drops from A+B to A+B/2, the weight fetches from L2 halve, and the MMA
+// instruction count per pixel halves.  The leader CTA (cluster rank 0) issues the MMAs; both CTAs'
+// TMA loads complete on the leader's mbarriers (cp.async.bulk.tensor ... .cta_group::2), and
+// tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs.
+constexpr int kB2Stages = 6;
+constexpr uint32_t kB2StageBytes = 64 * 128;   // half of an (at most) 128-row block
+
+template <int NACC> struct Tc2Cfg {
+  static constexpr int kPatchRowsMax = NACC * kTcRowsPerAcc + 4;
+  static constexpr uint32_t kPatchBytes = kPatchRowsMax * kTcTileW * 128;
+  static constexpr int kPatchStages = NACC == 4 ? 2 : (NACC == 2 ? 3 : 4);
+  static constexpr uint32_t kSmemBytes = kPatchStages * kPatchBytes + kB2Stages * kB2StageBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0,
+                                                int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+struct Tile2 { int job, n, y0, x0, valid, nacc; };
+// Work item -> this CTA's tile.  Items [0, main_tiles) are pair-tiles (tiles 2q and 2q+1 of a job);
+// the pair-tiles of the last partial wave are handed out as NACC single-sub-tile items each.
+__device__ __forceinline__ Tile2 decode_tile2(const TcKParams& p, int item, int rank, int nacc_full) {
+  Tile2 r;
+  int pt = item, sub = 0;
+  r.nacc = nacc_full;
+  if (item >= p.main_tiles) {
+    const int k = item - p.main_tiles;
+    pt = p.main_tiles + k / nacc_full;
+    sub = k - (k / nacc_full) * nacc_full;
+    r.nacc = 1;
+  }
+  const int ppj = (p.tiles_per_job + 1) >> 1;        // pair-tiles per job
+  r.job = pt / ppj;
+  int t = 2 * (pt - r.job * ppj) + rank;
+  r.valid = t < p.tiles_per_job;
+  if (!r.valid) t = p.tiles_per_job - 1;             // odd tile count: the peer recomputes the last tile, stores nothing
+  const int per_frame = p.tiles_x * p.tiles_y;
+  r.n = t / per_frame;
+  t -= r.n * per_frame;
+  r.y0 = (t / p.tiles_x) * (nacc_full * kTcRowsPerAcc) + sub * kTcRowsPerAcc;
+  r.x0 = (t % p.tiles_x) * kTcTileW;
+  if (r.y0 >= p.H) { r.valid = 0; r.y0 = 0; }        // empty sub-tile of a split tail tile: compute, store nothing
+  return r;
+}
+
+template <int NACC, int OPERAND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap bmap0,
+                const __grid_constant__ CUtensorMap bmap1, const __grid_constant__ TcKParams p) {
+  using OutT = typename OperandTraits<OPERAND>::Out;
+  using Cfg = Tc2Cfg<NACC>;
+  constexpr int NPB = Cfg::kPatchStages;
+  constexpr uint32_t ROW_BYTES = kTcTileW * 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_patch = sbase;
+  const uint32_t s_b = sbase + NPB * Cfg::kPatchBytes;
+  const uint32_t s_bar = s_b + kB2Stages * kB2StageBytes;
+  const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * NPB;
+  const uint32_t bar_b_full = s_bar + 16 * NPB, bar_b_empty = bar_b_full + 8 * kB2Stages;
+  const uint32_t bar_acc_full = bar_b_empty + 8 * kB2Stages, bar_acc_empty = bar_acc_full + 16;
+  const uint32_t s_tmem_slot = bar_acc_empty + 16;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (s_tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int total_items = p.total_items;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap1) : "memory");
+    for (int i = 0; i < NPB; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
+    for (int i = 0; i < kB2Stages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem_slot), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================================ producer (both CTAs) ======================================
+    int ps = 0, bs = 0;
+    uint32_t pph = 0, bph = 0;
+    for (int item = cluster_id; item < total_items; item += nclusters) {
+      const Tile2 tl = decode_tile2(p, item, (int)rank, NACC);
+      const TcJob& job = p.job[tl.job];
+      const CUtensorMap* bm = tl.job ? &bmap1 : &bmap0;
+      for (int s = 0; s < p.nslab; ++s) {
+        for (int dxi = 0; dxi < p.ndx; ++dxi) {
+          mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(bar_patch_full + 8 * ps, 2 * p.patch_tx);
+            tma_load_4d_2sm(s_patch + ps * Cfg::kPatchBytes, &tmap, mapa_u32(bar_patch_full + 8 * ps, 0),
+                            job.in_coff + s * p.slab_elems, tl.x0 + p.dx_ord[dxi] - p.pad, tl.y0 - p.pad, tl.n);
+          }
+          __syncwarp();
+          if (++ps == NPB) { ps = 0; pph ^= 1; }
+          for (int dyi = 0; dyi < p.ndy; ++dyi) {
+            mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
+            if (elect_one()) {
+              const uint32_t bytes = p.b_bytes[dxi][dyi], half = bytes >> 1;
+              if (leader) mbar_expect_tx(bar_b_full + 8 * bs, bytes);
+              const uint32_t bar = mapa_u32(bar_b_full + 8 * bs, 0);
+              const int row0 = (int)(((uint32_t)s * p.slab_bytes + p.b_off[dxi][dyi] + rank * half) >> 7);
+              for (uint32_t part = 0; part < half; part += 4096)
+                tma_load_2d_2sm(s_b + bs * kB2StageBytes + part, bm, bar, 0, row0 + (int)(part >> 7));
+            }
+            __syncwarp();
+            if (++bs == kB2Stages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ===============================
+    if (leader) {
+      int ps = 0, bs = 0;
+      uint32_t pph = 0, bph = 0;
+      int it = 0;
+      const uint64_t desc_hi = umma_desc(0);
+      for (int item = cluster_id; item < total_items; item += nclusters, ++it) {
+        const Tile2 tl = decode_tile2(p, item, 0, NACC);
+        const int outer_col = p.job[tl.job].outer_col;
+        const int buf = it % p.nbuf;
+        const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
+        mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * NACC * p.n_cols);
+        uint32_t acc0 = 0;
+        for (int s = 0; s < p.nslab; ++s) {
+          for (int dxi = 0; dxi < p.ndx; ++dxi) {
+            mbar_wait(bar_patch_full + 8 * ps, pph);
+            const uint32_t patch = s_patch + ps * Cfg::kPatchBytes;
+            for (int dyi = 0; dyi < p.ndy; ++dyi) {
+              mbar_wait(bar_b_full + 8 * bs, bph);
+              tc_fence_after();
+              const bool half = p.b_bytes[dxi][dyi] < (uint32_t)p.n_cols * 128u;
+              const uint32_t idesc = half ? p.idesc_half : p.idesc_full;
+              const uint32_t d0 = d_base + (half ? (uint32_t)outer_col : 0u);
+              const uint64_t bdesc = desc_hi | (uint64_t)(((s_b + bs * kB2StageBytes) & 0x3FFFFu) >> 4);
+              const uint64_t adesc0 = desc_hi | (uint64_t)(((patch + (uint32_t)p.dy_ord[dyi] * ROW_BYTES) & 0x3FFFFu) >> 4);
+              if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < NACC; ++j) {
+                  if (j >= tl.nacc) break;
+                  const uint64_t adesc = adesc0 + (uint64_t)(j * kTcRowsPerAcc * (ROW_BYTES >> 4));
+                  const uint32_t d = d0 + (uint32_t)(j * p.n_cols);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    if (OPERAND == TC_TF32) umma_tf32_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? acc0 : 1u);
+                    else                    umma_f16_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? acc0 : 1u);
+                  }
+                }
+                umma_commit_2sm(bar_b_empty + 8 * bs);
+                if (dyi == p.ndy - 1) umma_commit_2sm(bar_patch_empty + 8 * ps);
+                if (dyi == p.ndy - 1 && dxi == p.ndx - 1 && s == p.nslab - 1) umma_commit_2sm(bar_acc_full + 8 * buf);
+              }
+              __syncwarp();
+              acc0 = 1;
+              if (++bs == kB2Stages) { bs = 0; bph ^= 1; }
+            }
+            if (++ps == NPB) { ps = 0; pph ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue (both CTAs, own tile) ==============================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int my = m / kTcTileW, mx = m % kTcTileW;
+    const uint32_t acc_empty_leader = mapa_u32(bar_acc_empty, 0);
+    int it = 0;
+    for (int item = cluster_id; item < total_items; item += nclusters, ++it) {
+      const Tile2 tl = decode_tile2(p, item, (int)rank, NACC);
+      const TcJob& job = p.job[tl.job];
+      const int buf = it % p.nbuf;
+      mbar_wait(bar_acc_full + 8 * buf, (uint32_t)(it / p.nbuf) & 1u);
+      tc_fence_after();
+      const int px = tl.x0 + mx;
+      const int cpa = p.n_cols >> 5, nchunk = tl.nacc * cpa;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NACC * p.n_cols);
+      auto issue = [&](int i, uint32_t (&r)[32]) { tmem_ld32(lane_base + (uint32_t)(i << 5), r); };
+      auto drain = [&](int i, const uint32_t (&r)[32]) {
+        const int j = i / cpa, c0 = (i - j * cpa) << 5;
+        const int py = tl.y0 + j * kTcRowsPerAcc + my;
+        if (tl.valid && (py < p.H) && (px < p.W)) {
+          const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
+          store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32);
+        }
+      };
+      uint32_t ra[32], rb[32];
+      issue(0, ra);
+#pragma unroll 1
+      for (int i = 0; i < nchunk; i += 2) {
+        tmem_ld_wait();
+        issue(i + 1, rb);
+        drain(i, ra);
+        tmem_ld_wait();
+        if (i + 2 < nchunk) issue(i + 2, ra);
+        drain(i + 1, rb);
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(acc_empty_leader + 8 * buf);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // nobody frees TMEM or exits while the pair may still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host helpers
 
-uint32_t make_idesc(int operand, int n) {
+uint32_t make_idesc(int operand, int n, int m = 128) {
   // UMMA instruction descriptor: D = F32 (bits 4-5 = 1), A/B format (bits 7-9 / 10-12), both K-major,
-  // N >> 3 at bit 17, M >> 4 at bit 24 (M = 128).
+  // N >> 3 at bit 17, M >> 4 at bit 24 (M = 128, or 256 for cta_group::2).
   return (1u << 4) | ((uint32_t)operand << 7) | ((uint32_t)operand << 10) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(128 >> 4) << 24);
+         ((uint32_t)(m >> 4) << 24);
 }
 
 inline uint16_t f32_to_bf16(float f) {
@@ -568,7 +848,63 @@ cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, i
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// 2-D view of a packed weight stream for the 2-CTA kernel: rows of 128 bytes, box = 32 rows (4 KB),
+// no swizzle (the stream already holds the SWIZZLE_128B shared-memory image).
+cudaError_t tc_encode_bmap(CUtensorMap* map, const void* base, size_t bytes) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess) return e;
+  if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+  const cuuint64_t dims[2] = {128, (cuuint64_t)(bytes / 128)};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {128, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = reinterpret_cast<EncodeFn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims,
+                                                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 namespace {
+template <int NACC, int OPERAND>
+cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& b0, const CUtensorMap& b1, TcKParams& kp,
+                         cudaStream_t st) {
+  using Cfg = Tc2Cfg<NACC>;
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NACC, OPERAND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const int tile_h = NACC * kTcRowsPerAcc;
+  kp.tiles_y = cdiv(kp.H, tile_h);
+  kp.tiles_per_job = kp.B * kp.tiles_x * kp.tiles_y;
+  kp.total_tiles = kp.tiles_per_job * kp.njobs;
+  kp.nbuf = (2 * NACC * kp.n_cols <= 512) ? 2 : 1;
+  kp.patch_tx = (uint32_t)(tile_h + kp.ks - 1) * kTcTileW * 128u;
+  const int items = ((kp.tiles_per_job + 1) / 2) * kp.njobs;     // pair-tiles
+  int clusters = num_sms / 2;
+  if (items < clusters) clusters = items;
+  {
+    const int rem = items % clusters;
+    const bool split = NACC > 1 && items > clusters && cdiv(rem * NACC, clusters) < NACC;
+    kp.main_tiles = split ? items - rem : items;
+    kp.total_items = kp.main_tiles + (items - kp.main_tiles) * NACC;
+  }
+  conv_tc2_kernel<NACC, OPERAND><<<2 * clusters, kThreads, Cfg::kSmemBytes, st>>>(tmap, b0, b1, kp);
+  return cudaGetLastError();
+}
+
 template <int NACC, int OPERAND>
 cudaError_t launch_nacc(const CUtensorMap& tmap, TcKParams& kp, cudaStream_t st) {
   using Cfg = TcCfg<NACC>;
@@ -616,8 +952,9 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const TcConvPlan& plan, cons
   memcpy(kp.b_off, plan.b_off, sizeof(kp.b_off));
   kp.slab_bytes = plan.slab_bytes;
   kp.n_cols = plan.n_cols;
-  kp.idesc_full = make_idesc(plan.operand, plan.n_cols);
-  kp.idesc_half = make_idesc(plan.operand, 64);
+  const int mma_m = L.two_cta ? 256 : 128;
+  kp.idesc_full = make_idesc(plan.operand, plan.n_cols, mma_m);
+  kp.idesc_half = make_idesc(plan.operand, 64, mma_m);
   kp.relu = L.relu; kp.out_act = L.out_act; kp.is_tf32 = plan.operand == TC_TF32;
   {
     static int dbg = -1;
@@ -626,6 +963,25 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const TcConvPlan& plan, cons
   }
   if (L.out_act != (plan.operand == TC_TF32 ? ACT_F32 : plan.operand == TC_BF16 ? ACT_BF16 : ACT_F16))
     return cudaErrorInvalidValue;   // activations are stored in the operand type
+  if (L.two_cta) {
+    if (!L.bmap[0] || (L.njobs > 1 && !L.bmap[1])) return cudaErrorInvalidValue;
+    const CUtensorMap& b0 = *L.bmap[0];
+    const CUtensorMap& b1 = *L.bmap[L.njobs > 1 ? 1 : 0];
+#define CODON_TC2_DISPATCH(N)                                                  \
+  switch (plan.operand) {                                                      \
+    case TC_F16: return launch_nacc2<N, TC_F16>(tmap, b0, b1, kp, st);         \
+    case TC_BF16: return launch_nacc2<N, TC_BF16>(tmap, b0, b1, kp, st);       \
+    case TC_TF32: return launch_nacc2<N, TC_TF32>(tmap, b0, b1, kp, st);       \
+    default: return cudaErrorInvalidValue;                                     \
+  }
+    switch (L.nacc) {
+      case 1: CODON_TC2_DISPATCH(1)
+      case 2: CODON_TC2_DISPATCH(2)
+      case 4: CODON_TC2_DISPATCH(4)
+      default: return cudaErrorInvalidValue;
+    }
+#undef CODON_TC2_DISPATCH
+  }
 #define CODON_TC_DISPATCH(N)                                                   \
   switch (plan.operand) {                                                      \
     case TC_F16: return launch_nacc<N, TC_F16>(tmap, kp, st);                  \

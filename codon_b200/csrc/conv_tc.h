@@ -60,6 +60,8 @@ struct TcLaunch {
   int relu = 0;
   int out_act = 0;             // ActType of out / res
   int nacc = 4;                // accumulators (128-pixel sub-tiles) per CTA tile: 1, 2 or 4
+  int two_cta = 0;             // 1: cluster-of-2 kernel (tcgen05 cta_group::2, M = 256); needs bmap
+  const CUtensorMap* bmap[2] = {nullptr, nullptr};   // per job: 2-D map of the packed weight stream
 };
 
 // Box height (image rows) the A tensor map must be encoded with for this plan / nacc.
@@ -68,6 +70,9 @@ inline int tc_box_rows(const TcConvPlan& p, int nacc) { return nacc * kTcRowsPer
 // Encodes the 4-D NHWC tensor map {C, W, H, B} with box {slab_elems, 16, box_rows, 1}, SWIZZLE_128B.
 cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, int W, int H, int B,
                            int slab_elems, int box_rows);
+
+// 2-D tensor map over a packed weight stream (rows of 128 B, 32-row boxes) for the 2-CTA kernel.
+cudaError_t tc_encode_bmap(CUtensorMap* map, const void* base, size_t bytes);
 
 cudaError_t launch_conv_tc(const CUtensorMap& tmap, const TcConvPlan& plan, const TcLaunch& L,
                            cudaStream_t st);
