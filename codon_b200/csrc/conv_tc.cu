@@ -372,11 +372,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const int px = tl.x0 + mx;
       // software-pipelined drain: the TMEM load of chunk i+1 is in flight while chunk i is converted
       // and stored (chunk = 32 accumulator columns of one 128-pixel sub-tile)
-      const int cpa = p.n_cols >> 5, nchunk = tl.nacc * cpa;
+      const int cpa_sh = p.n_cols == 128 ? 2 : 1, nchunk = tl.nacc << cpa_sh;    // chunks per accumulator: 4 or 2
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NACC * p.n_cols);
       auto issue = [&](int i, uint32_t (&r)[32]) { tmem_ld32(lane_base + (uint32_t)(i << 5), r); };
       auto drain = [&](int i, const uint32_t (&r)[32]) {
-        const int j = i / cpa, c0 = (i - j * cpa) << 5;
+        const int j = i >> cpa_sh, c0 = (i - (j << cpa_sh)) << 5;
         const int py = tl.y0 + j * kTcRowsPerAcc + my;
         if ((py < p.H) && (px < p.W) && !(p.debug & 1)) {
           const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
@@ -416,6 +416,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 // instruction count per pixel halves.  The leader CTA (cluster rank 0) issues the MMAs; both CTAs'
 // TMA loads complete on the leader's mbarriers (cp.async.bulk.tensor ... .cta_group::2), and
 // tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs.
+constexpr int kThreads2 = 224;   // warp 0 A producer, 1 MMA, 2-5 epilogue, 6 B producer
 constexpr int kB2Stages = 6;
 constexpr uint32_t kB2StageBytes = 64 * 128;   // half of an (at most) 128-row block
 
@@ -439,8 +440,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Arrive on a (possibly remote) mbarrier of the cluster.  Relaxed: the only thing the waiter (the MMA
+// issuer) may touch afterwards is TMEM, whose reads were completed by tcgen05.wait::ld and ordered by
+// tcgen05.fence::before_thread_sync; a release at cluster scope would drain every outstanding global
+// store of the epilogue first (MEMBAR.ALL + ERRBAR, ~15 % of the epilogue in the r01b profile).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0,
                                                 int c1, int c2, int c3) {
@@ -505,7 +510,7 @@ __device__ __forceinline__ Tile2 decode_tile2(const TcKParams& p, int item, int 
 }
 
 template <int NACC, int OPERAND>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap bmap0,
                 const __grid_constant__ CUtensorMap bmap1, const __grid_constant__ TcKParams p) {
   using OutT = typename OperandTraits<OPERAND>::Out;
@@ -552,32 +557,45 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ================================ producer (both CTAs) ======================================
-    int ps = 0, bs = 0;
-    uint32_t pph = 0, bph = 0;
+    // ================================ A producer (both CTAs): activation patches =================
+    int ps = 0;
+    uint32_t pph = 0;
+    const uint32_t full_leader = mapa_u32(bar_patch_full, 0);
     for (int item = cluster_id; item < total_items; item += nclusters) {
       const Tile2 tl = decode_tile2(p, item, (int)rank, NACC);
-      const TcJob& job = p.job[tl.job];
-      const CUtensorMap* bm = tl.job ? &bmap1 : &bmap0;
+      const int coff = p.job[tl.job].in_coff;
       for (int s = 0; s < p.nslab; ++s) {
         for (int dxi = 0; dxi < p.ndx; ++dxi) {
           mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
           if (elect_one()) {
             if (leader) mbar_expect_tx(bar_patch_full + 8 * ps, 2 * p.patch_tx);
-            tma_load_4d_2sm(s_patch + ps * Cfg::kPatchBytes, &tmap, mapa_u32(bar_patch_full + 8 * ps, 0),
-                            job.in_coff + s * p.slab_elems, tl.x0 + p.dx_ord[dxi] - p.pad, tl.y0 - p.pad, tl.n);
+            tma_load_4d_2sm(s_patch + ps * Cfg::kPatchBytes, &tmap, full_leader + 8 * ps,
+                            coff + s * p.slab_elems, tl.x0 + p.dx_ord[dxi] - p.pad, tl.y0 - p.pad, tl.n);
           }
           __syncwarp();
           if (++ps == NPB) { ps = 0; pph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ================================ B producer (both CTAs): this CTA's half of every weight block
+    int bs = 0;
+    uint32_t bph = 0;
+    const uint32_t full_leader = mapa_u32(bar_b_full, 0);
+    for (int item = cluster_id; item < total_items; item += nclusters) {
+      const Tile2 tl = decode_tile2(p, item, (int)rank, NACC);
+      const CUtensorMap* bm = tl.job ? &bmap1 : &bmap0;
+      for (int s = 0; s < p.nslab; ++s) {
+        for (int dxi = 0; dxi < p.ndx; ++dxi) {
           for (int dyi = 0; dyi < p.ndy; ++dyi) {
             mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
             if (elect_one()) {
               const uint32_t bytes = p.b_bytes[dxi][dyi], half = bytes >> 1;
               if (leader) mbar_expect_tx(bar_b_full + 8 * bs, bytes);
-              const uint32_t bar = mapa_u32(bar_b_full + 8 * bs, 0);
               const int row0 = (int)(((uint32_t)s * p.slab_bytes + p.b_off[dxi][dyi] + rank * half) >> 7);
-              for (uint32_t part = 0; part < half; part += 4096)
-                tma_load_2d_2sm(s_b + bs * kB2StageBytes + part, bm, bar, 0, row0 + (int)(part >> 7));
+              const uint32_t dst = s_b + bs * kB2StageBytes;
+              tma_load_2d_2sm(dst, bm, full_leader + 8 * bs, 0, row0);
+              if (half > 4096) tma_load_2d_2sm(dst + 4096, bm, full_leader + 8 * bs, 0, row0 + 32);
             }
             __syncwarp();
             if (++bs == kB2Stages) { bs = 0; bph ^= 1; }
@@ -652,11 +670,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       mbar_wait(bar_acc_full + 8 * buf, (uint32_t)(it / p.nbuf) & 1u);
       tc_fence_after();
       const int px = tl.x0 + mx;
-      const int cpa = p.n_cols >> 5, nchunk = tl.nacc * cpa;
+      const int cpa_sh = p.n_cols == 128 ? 2 : 1, nchunk = tl.nacc << cpa_sh;    // chunks per accumulator: 4 or 2
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NACC * p.n_cols);
       auto issue = [&](int i, uint32_t (&r)[32]) { tmem_ld32(lane_base + (uint32_t)(i << 5), r); };
       auto drain = [&](int i, const uint32_t (&r)[32]) {
-        const int j = i / cpa, c0 = (i - j * cpa) << 5;
+        const int j = i >> cpa_sh, c0 = (i - (j << cpa_sh)) << 5;
         const int py = tl.y0 + j * kTcRowsPerAcc + my;
         if (tl.valid && (py < p.H) && (px < p.W)) {
           const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
@@ -901,7 +919,7 @@ cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& b0, const C
     kp.main_tiles = split ? items - rem : items;
     kp.total_items = kp.main_tiles + (items - kp.main_tiles) * NACC;
   }
-  conv_tc2_kernel<NACC, OPERAND><<<2 * clusters, kThreads, Cfg::kSmemBytes, st>>>(tmap, b0, b1, kp);
+  conv_tc2_kernel<NACC, OPERAND><<<2 * clusters, kThreads2, Cfg::kSmemBytes, st>>>(tmap, b0, b1, kp);
   return cudaGetLastError();
 }
 
