@@ -80,9 +80,9 @@ struct codon_ctx {
 
   // tensor-map cache (valid while workspace / shape unchanged)
   struct MapKey {
-    const void* base; int C, box_rows, B, H, W;
+    const void* base; int C, box_w, box_h, B, H, W;
     bool operator<(const MapKey& o) const {
-      return std::tie(base, C, box_rows, B, H, W) < std::tie(o.base, o.C, o.box_rows, o.B, o.H, o.W);
+      return std::tie(base, C, box_w, box_h, B, H, W) < std::tie(o.base, o.C, o.box_w, o.box_h, o.B, o.H, o.W);
     }
   };
   std::map<MapKey, CUtensorMap> tmaps;
@@ -192,16 +192,16 @@ std::vector<float> to_tap_major(const HostTensor& t, int cout, int cin, int ks) 
   return r;
 }
 
-int get_tmap(codon_ctx* ctx, const void* base, int C, int box_rows, int slab_elems, int B, int H, int W,
+int get_tmap(codon_ctx* ctx, const void* base, int C, int box_w, int box_h, int slab_elems, int B, int H, int W,
              const CUtensorMap** out) {
   codon_ctx::MapKey key;
   memset(&key, 0, sizeof(key));
-  key.base = base; key.C = C; key.box_rows = box_rows; key.B = B; key.H = H; key.W = W;
+  key.base = base; key.C = C; key.box_w = box_w; key.box_h = box_h; key.B = B; key.H = H; key.W = W;
   auto it = ctx->tmaps.find(key);
   if (it == ctx->tmaps.end()) {
     if (ctx->tmaps.size() > 256) ctx->tmaps.clear();
     CUtensorMap m;
-    CU_TRY(ctx, tc_encode_tmap(&m, base, ctx->act, C, W, H, B, slab_elems, box_rows));
+    CU_TRY(ctx, tc_encode_tmap(&m, base, ctx->act, C, W, H, B, slab_elems, box_w, box_h));
     it = ctx->tmaps.emplace(key, m).first;
   }
   *out = &it->second;
@@ -217,9 +217,8 @@ int pick_nacc(int B, int H, int W, int njobs, int prefer, const char* env = null
     const char* e = getenv(env);
     if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) return atoi(e);
   }
-  const int tx = cdiv(W, kTcTileW);
   for (int nacc = prefer; nacc > 1; nacc >>= 1) {
-    const long tiles = (long)B * tx * cdiv(H, nacc * kTcRowsPerAcc) * njobs;
+    const long tiles = (long)B * cdiv(W, tc_tile_w(nacc)) * cdiv(H, tc_tile_h(nacc)) * njobs;
     if (tiles >= 2 * 148) return nacc;
   }
   return 1;
@@ -230,7 +229,7 @@ int use_two_cta(int B, int H, int W, int nacc) {
   static int env = -2;
   if (env == -2) { const char* e = getenv("CODON_TC_2CTA"); env = e ? atoi(e) : -1; }
   if (env == 0 || env == 1) return env;
-  const long tiles = (long)B * cdiv(W, kTcTileW) * cdiv(H, nacc * kTcRowsPerAcc);
+  const long tiles = (long)B * cdiv(W, tc_tile_w(nacc)) * cdiv(H, tc_tile_h(nacc));
   return tiles >= 148 ? 1 : 0;
 }
 
@@ -275,7 +274,7 @@ struct Runner {
     // the HBM-bound 1x1 / 3x3 layers measured slower in cluster mode; the 5x5 layers gain 15-20 %
     L.two_cta = ks == 5 ? use_two_cta(B, H, W, L.nacc) : 0;
     const CUtensorMap* tm = nullptr;
-    int rc = get_tmap(ctx, ws + in, in_C, tc_box_rows(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
+    int rc = get_tmap(ctx, ws + in, in_C, tc_box_w(l0.plan, L.nacc), tc_box_h(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
     if (rc) return rc;
     ProfScope ps(ctx, cat_of(cin, cout, ks), flops, st);
     CU_TRY(ctx, launch_conv_tc(*tm, l0.plan, L, st));
@@ -320,7 +319,7 @@ struct Runner {
     }
     L.two_cta = use_two_cta(B, H, W, L.nacc);
     const CUtensorMap* tm = nullptr;
-    int rc = get_tmap(ctx, ws + in, in_C, tc_box_rows(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
+    int rc = get_tmap(ctx, ws + in, in_C, tc_box_w(l0.plan, L.nacc), tc_box_h(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
     if (rc) return rc;
     ProfScope ps(ctx, PC_PAIR, 2.0 * B * H * W * 64.0 * 64.0 * 34.0 * njobs, st);
     CU_TRY(ctx, launch_conv_tc(*tm, l0.plan, L, st));

@@ -6,22 +6,26 @@
 // (:75-80, :123-125) is ONE launch that writes the 128-channel concat directly.
 //
 // GEMM view: M = pixels, N = output channels (64 or 128), K = taps x input channels.
-//   * A (activations): a CTA owns a tile of 16 x (8*NACC) pixels.  For every 128-byte channel
-//     slab and every horizontal tap offset dx, ONE 4-D TMA box {slab, 16 px, 8*NACC + ks - 1 rows}
-//     lands a halo patch in shared memory (SWIZZLE_128B, one pixel = one 128-B row; out-of-image
-//     pixels are zero-filled by TMA, which is exactly the layer's zero padding).  The ks vertical
-//     taps dy and the NACC 128-pixel sub-tiles then address that one patch through UMMA
-//     descriptors offset by whole 2-KB image rows (1024-B aligned, so the swizzle phase is
-//     unchanged).  A traffic is therefore ~(1 + (ks-1)/(8*NACC)) x ks patches per tile instead of
-//     ks*ks im2col tiles per sub-tile.
+//   * A (activations): an accumulator covers a sub-tile of 8 x 16 pixels (M = 128, row m = y*8 + x);
+//     a CTA tile is NAX x NAY sub-tiles (NACC = 1, 2 or 4).  For every 128-byte channel slab ONE 4-D
+//     TMA box {slab, tile_w + ks - 1 px, tile_h + ks - 1 rows} lands a halo patch in shared memory
+//     (SWIZZLE_128B, one pixel = one 128-B row; out-of-image pixels are zero-filled by TMA, which is
+//     exactly the layer's zero padding).  Every tap (dx, dy) of every sub-tile then reads that one
+//     patch through a UMMA descriptor whose start address is shifted by (dy * pitch + dx) pixels and
+//     whose 8-row-group stride (SBO) is the patch row pitch: the hardware applies the 128-B swizzle
+//     on absolute shared-memory address bits (verified by tools/umma_shift_test.cu), so a shifted
+//     start address reads exactly what TMA wrote.  A traffic is one patch per slab and tile
+//     ((T+k-1)^2 / T^2 of the input) instead of k*k im2col tiles.
 //   * B (weights): host-packed per (slab, tap) K-major blocks already in the SWIZZLE_128B image,
-//     fetched with cp.async.bulk into a 4-deep ring; each block is reused by NACC MMAs groups.
+//     streamed through a ring of stages; each block feeds NACC x 4 MMAs.
 //   * D: NACC accumulators of 128 lanes x N fp32 columns in TMEM; double-buffered across tiles
 //     when 2*NACC*N <= 512 so the epilogue of tile i overlaps the main loop of tile i+1.
-//   * Roles (192 threads): warp 0 = TMA/bulk producer (one lane), warp 1 = TMEM owner + MMA issuer
-//     (one lane, tcgen05.mma.cta_group::1 M=128), warps 2..5 = epilogue (tcgen05.ld 32x32b ->
-//     ReLU / residual / convert -> 16-byte global stores).  mbarrier pipelines throughout;
-//     persistent CTAs stride over the tile list.
+//   * conv_tc_kernel (1 CTA): warp 0 producer, warp 1 TMEM owner + MMA issuer, warps 2..5 epilogue.
+//     conv_tc2_kernel (cluster of 2 CTAs, tcgen05 cta_group::2, M = 256): see below.
+//   * The producer / MMA loops are warp-uniform and one elect.sync lane issues (no per-thread
+//     waterfall loops around UTCHMMA / UTMALDG); mbarrier pipelines throughout; persistent CTAs
+//     stride over the tile list, and the tiles of the last partial wave are split into single
+//     sub-tile items.
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -34,9 +38,14 @@ namespace codon {
 
 namespace {
 
+constexpr int kNPB = 2;                        // patch stages
 constexpr int kBStages = 4;
 constexpr uint32_t kBStageBytes = 128 * 128;   // up to 128 rows x 128 B
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                  // warp 0 producer, 1 MMA, 2-9 epilogue (two warps per TMEM lane quarter)
+constexpr int kThreads2 = 352;                 // warp 0 A producer, 1 MMA, 2-9 epilogue, 10 B producer
+constexpr int kB2Stages = 8;
+constexpr uint32_t kB2StageBytes = 64 * 128;   // half of an (at most) 128-row block
+constexpr uint32_t kBarBytes = 1024;           // barrier block at the start of the dynamic smem
 
 struct TcKParams {
   TcJob job[2];
@@ -49,15 +58,14 @@ struct TcKParams {
   int n_cols;
   uint32_t idesc_full, idesc_half;
   int relu, out_act, is_tf32, nbuf;
-  uint32_t patch_tx;
-  int debug;   // CODON_TC_DEBUG bits (perf experiments only): 1 no epilogue stores, 2 no B loads, 4 no A loads, 8 no MMAs
+  int pw;                        // patch width in pixels (tile_w + ks - 1); the patch row pitch is pw * 128 B
+  uint32_t patch_tx, patch_stage;   // bytes of one patch (TMA transaction) and of one patch stage (1024-aligned)
+  int debug;   // CODON_TC_DEBUG bits (perf experiments only, 1-CTA kernel): 1 no epilogue stores, 2 no B loads, 4 no A loads, 8 no MMAs, 16 no waits
 };
 
-template <int NACC> struct TcCfg {
-  static constexpr int kPatchRowsMax = NACC * kTcRowsPerAcc + 4;
-  static constexpr uint32_t kPatchBytes = kPatchRowsMax * kTcTileW * 128;
-  static constexpr int kPatchStages = NACC == 4 ? 2 : (NACC == 2 ? 3 : 4);
-  static constexpr uint32_t kSmemBytes = kPatchStages * kPatchBytes + kBStages * kBStageBytes + 1024 + 256;
+template <int NACC> struct Geo {
+  static constexpr int NAX = NACC >= 2 ? 2 : 1, NAY = NACC / NAX;
+  static constexpr int TW = NAX * kTcSubW, TH = NAY * kTcSubH;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -166,18 +174,20 @@ template <> struct OperandTraits<TC_F16> { using Out = __half; };
 template <> struct OperandTraits<TC_BF16> { using Out = __nv_bfloat16; };
 template <> struct OperandTraits<TC_TF32> { using Out = float; };
 
-struct Tile { int job, n, y0, x0, nacc; };
-// Work item -> tile.  Full tiles hold NACC vertically adjacent 128-pixel sub-tiles.  The tiles of the
-// last, partial wave (total_tiles % gridDim of them) are handed out as NACC separate single
-// sub-tile items instead, so the tail of the launch costs ~1/NACC of a wave.
-__device__ __forceinline__ Tile decode_tile(const TcKParams& p, int item, int nacc_full) {
+struct Tile { int job, n, y0, x0, nacc, valid; };
+// Work item -> tile.  Full tiles hold NACC sub-tiles (NAX x NAY).  The tiles of the last, partial
+// wave are handed out as NACC separate single-sub-tile items, so the tail of the launch costs ~1/NACC
+// of a wave.
+template <int NACC>
+__device__ __forceinline__ Tile decode_tile(const TcKParams& p, int item) {
+  using G = Geo<NACC>;
   Tile r;
   int t = item, sub = 0;
-  r.nacc = nacc_full;
+  r.nacc = NACC;
   if (item >= p.main_tiles) {
     const int k = item - p.main_tiles;
-    t = p.main_tiles + k / nacc_full;
-    sub = k - (k / nacc_full) * nacc_full;
+    t = p.main_tiles + k / NACC;
+    sub = k - (k / NACC) * NACC;
     r.nacc = 1;
   }
   r.job = t / p.tiles_per_job;
@@ -185,10 +195,21 @@ __device__ __forceinline__ Tile decode_tile(const TcKParams& p, int item, int na
   const int per_frame = p.tiles_x * p.tiles_y;
   r.n = q / per_frame;
   q -= r.n * per_frame;
-  r.y0 = (q / p.tiles_x) * (nacc_full * kTcRowsPerAcc) + sub * kTcRowsPerAcc;
-  r.x0 = (q % p.tiles_x) * kTcTileW;
+  r.y0 = (q / p.tiles_x) * G::TH + (sub / G::NAX) * kTcSubH;
+  r.x0 = (q % p.tiles_x) * G::TW + (sub % G::NAX) * kTcSubW;
+  r.valid = (r.y0 < p.H) && (r.x0 < p.W);
   return r;
 }
+
+// K-major SWIZZLE_128B descriptor with a zero start address and the given 8-row-group stride.
+__device__ __forceinline__ uint64_t umma_desc_hi(uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_addr(uint32_t saddr) { return (uint64_t)((saddr & 0x3FFFFu) >> 4); }
 
 // Epilogue of one 32-channel chunk held by one thread (one pixel).
 template <typename T>
@@ -223,31 +244,29 @@ template <int NACC, int OPERAND>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcKParams p) {
   using OutT = typename OperandTraits<OPERAND>::Out;
-  using Cfg = TcCfg<NACC>;
-  constexpr int NPB = Cfg::kPatchStages;
-  constexpr int TILE_H = NACC * kTcRowsPerAcc;
-  constexpr uint32_t ROW_BYTES = kTcTileW * 128;   // one image row of a patch
+  using G = Geo<NACC>;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_patch = sbase;
-  const uint32_t s_b = sbase + NPB * Cfg::kPatchBytes;
-  const uint32_t s_bar = s_b + kBStages * kBStageBytes;
+  const uint32_t s_bar = sbase;
+  const uint32_t s_patch = sbase + kBarBytes;
+  const uint32_t s_b = s_patch + kNPB * p.patch_stage;
   // barrier map (8 B each)
-  const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * NPB;
-  const uint32_t bar_b_full = s_bar + 16 * NPB, bar_b_empty = bar_b_full + 8 * kBStages;
+  const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * kNPB;
+  const uint32_t bar_b_full = s_bar + 16 * kNPB, bar_b_empty = bar_b_full + 8 * kBStages;
   const uint32_t bar_acc_full = bar_b_empty + 8 * kBStages, bar_acc_empty = bar_acc_full + 16;
   const uint32_t s_tmem_slot = bar_acc_empty + 16;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (s_tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t pitch = (uint32_t)p.pw * 128u;    // patch row pitch in bytes
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-    for (int i = 0; i < NPB; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
+    for (int i = 0; i < kNPB; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
     for (int i = 0; i < kBStages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -265,23 +284,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     int ps = 0, bs = 0;
     uint32_t pph = 0, bph = 0;
     for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
-      const Tile tl = decode_tile(p, t, NACC);
-      if (tl.y0 >= p.H) continue;                 // empty sub-tile of a split tail tile
+      const Tile tl = decode_tile<NACC>(p, t);
+      if (!tl.valid) continue;                    // empty sub-tile of a split tail tile
       const TcJob& job = p.job[tl.job];
       for (int s = 0; s < p.nslab; ++s) {
         const uint8_t* wslab = job.w + (size_t)s * p.slab_bytes;
-        for (int dxi = 0; dxi < p.ndx; ++dxi) {
-          mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
-          if (elect_one()) {
-            if (p.debug & 4) mbar_arrive(bar_patch_full + 8 * ps);
-            else {
-              mbar_expect_tx(bar_patch_full + 8 * ps, p.patch_tx);
-              tma_load_4d(s_patch + ps * Cfg::kPatchBytes, &tmap, bar_patch_full + 8 * ps,
-                          job.in_coff + s * p.slab_elems, tl.x0 + p.dx_ord[dxi] - p.pad, tl.y0 - p.pad, tl.n);
-            }
+        mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
+        if (elect_one()) {
+          if (p.debug & 4) mbar_arrive(bar_patch_full + 8 * ps);
+          else {
+            mbar_expect_tx(bar_patch_full + 8 * ps, p.patch_tx);
+            tma_load_4d(s_patch + ps * p.patch_stage, &tmap, bar_patch_full + 8 * ps,
+                        job.in_coff + s * p.slab_elems, tl.x0 - p.pad, tl.y0 - p.pad, tl.n);
           }
-          __syncwarp();
-          if (++ps == NPB) { ps = 0; pph ^= 1; }
+        }
+        __syncwarp();
+        if (++ps == kNPB) { ps = 0; pph ^= 1; }
+        for (int dxi = 0; dxi < p.ndx; ++dxi) {
           for (int dyi = 0; dyi < p.ndy; ++dyi) {
             mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
             if (elect_one()) {
@@ -303,10 +322,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     int ps = 0, bs = 0;
     uint32_t pph = 0, bph = 0;
     int it = 0;
-    const uint64_t desc_hi = umma_desc(0);     // descriptor with a zero start address
+    const uint64_t desc_a = umma_desc_hi(pitch), desc_b = umma_desc_hi(1024);
     for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
-      const Tile tl = decode_tile(p, t, NACC);
-      if (tl.y0 >= p.H) continue;
+      const Tile tl = decode_tile<NACC>(p, t);
+      if (!tl.valid) continue;
       const int outer_col = p.job[tl.job].outer_col;
       const int buf = it % p.nbuf;
       const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
@@ -315,24 +334,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const uint32_t d_base = tmem_base + (uint32_t)(buf * NACC * p.n_cols);
       uint32_t acc0 = 0;                        // 0 only for the very first MMA group of the tile
       for (int s = 0; s < p.nslab; ++s) {
+        if (!(p.debug & 16)) mbar_wait(bar_patch_full + 8 * ps, pph);
+        const uint32_t patch = s_patch + ps * p.patch_stage;
         for (int dxi = 0; dxi < p.ndx; ++dxi) {
-          if (!(p.debug & 16)) mbar_wait(bar_patch_full + 8 * ps, pph);
-          const uint32_t patch = s_patch + ps * Cfg::kPatchBytes;
           for (int dyi = 0; dyi < p.ndy; ++dyi) {
             if (!(p.debug & 16)) mbar_wait(bar_b_full + 8 * bs, bph);
             tc_fence_after();
             const bool half = p.b_bytes[dxi][dyi] < (uint32_t)p.n_cols * 128u;
             const uint32_t idesc = half ? p.idesc_half : p.idesc_full;
             const uint32_t d0 = d_base + (half ? (uint32_t)outer_col : 0u);
-            const uint64_t bdesc = desc_hi | (uint64_t)(((s_b + bs * kBStageBytes) & 0x3FFFFu) >> 4);
-            const uint64_t adesc0 = desc_hi | (uint64_t)(((patch + (uint32_t)p.dy_ord[dyi] * ROW_BYTES) & 0x3FFFFu) >> 4);
+            const uint64_t bdesc = desc_b | desc_addr(s_b + bs * kBStageBytes);
+            // tap (dx, dy): the patch shifted by dy rows and dx pixels
+            const uint64_t adesc0 = desc_a | desc_addr(patch + (uint32_t)p.dy_ord[dyi] * pitch + (uint32_t)p.dx_ord[dxi] * 128u);
+            const bool last = (dxi == p.ndx - 1) && (dyi == p.ndy - 1);
             if (elect_one()) {
               if (!(p.debug & 8)) {
 #pragma unroll
                 for (int j = 0; j < NACC; ++j) {
                   if (j >= tl.nacc) break;
-                  // accumulator j = image rows [8j, 8j+8) of the tile: +8 patch rows = +16 KB = +1024 (16-B units)
-                  const uint64_t adesc = adesc0 + (uint64_t)(j * kTcRowsPerAcc * (ROW_BYTES >> 4));
+                  // sub-tile j = (jx, jy): + jy*16 patch rows + jx*8 pixels
+                  const uint64_t adesc = adesc0 + (uint64_t)(((j / G::NAX) * kTcSubH * pitch + (j % G::NAX) * kTcSubW * 128u) >> 4);
                   const uint32_t d = d0 + (uint32_t)(j * p.n_cols);
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
@@ -343,33 +364,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 }
               }
               umma_commit(bar_b_empty + 8 * bs);
-              if (dyi == p.ndy - 1) umma_commit(bar_patch_empty + 8 * ps);
-              if (dyi == p.ndy - 1 && dxi == p.ndx - 1 && s == p.nslab - 1) umma_commit(bar_acc_full + 8 * buf);
+              if (last) umma_commit(bar_patch_empty + 8 * ps);
+              if (last && s == p.nslab - 1) umma_commit(bar_acc_full + 8 * buf);
             }
             __syncwarp();
             acc0 = 1;
             if (++bs == kBStages) { bs = 0; bph ^= 1; }
           }
-          if (++ps == NPB) { ps = 0; pph ^= 1; }
         }
+        if (++ps == kNPB) { ps = 0; pph ^= 1; }
       }
       ++it;
     }
   } else {
     // ================================ epilogue =================================================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int ehalf = (warp - 2) >> 2;           // 0 / 1: which half of the chunks this warp drains
     const int m = q * 32 + lane;                 // accumulator row == pixel inside the sub-tile
-    const int my = m / kTcTileW, mx = m % kTcTileW;
+    const int my = m / kTcSubW, mx = m % kTcSubW;
     int it = 0;
     for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
-      const Tile tl = decode_tile(p, t, NACC);
-      if (tl.y0 >= p.H) continue;
+      const Tile tl = decode_tile<NACC>(p, t);
+      if (!tl.valid) continue;
       const TcJob& job = p.job[tl.job];
       const int buf = it % p.nbuf;
       const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
       mbar_wait(bar_acc_full + 8 * buf, aph);
       tc_fence_after();
-      const int px = tl.x0 + mx;
       // software-pipelined drain: the TMEM load of chunk i+1 is in flight while chunk i is converted
       // and stored (chunk = 32 accumulator columns of one 128-pixel sub-tile)
       const int cpa_sh = p.n_cols == 128 ? 2 : 1, nchunk = tl.nacc << cpa_sh;    // chunks per accumulator: 4 or 2
@@ -377,22 +398,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       auto issue = [&](int i, uint32_t (&r)[32]) { tmem_ld32(lane_base + (uint32_t)(i << 5), r); };
       auto drain = [&](int i, const uint32_t (&r)[32]) {
         const int j = i >> cpa_sh, c0 = (i - (j << cpa_sh)) << 5;
-        const int py = tl.y0 + j * kTcRowsPerAcc + my;
+        const int py = tl.y0 + (j / G::NAX) * kTcSubH + my, px = tl.x0 + (j % G::NAX) * kTcSubW + mx;
         if ((py < p.H) && (px < p.W) && !(p.debug & 1)) {
           const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
           store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32);
         }
       };
+      // the two warps of a lane quarter take the even / odd chunks
       uint32_t ra[32], rb[32];
-      issue(0, ra);
+      int i = ehalf;
+      issue(i, ra);
 #pragma unroll 1
-      for (int i = 0; i < nchunk; i += 2) {
+      while (true) {
         tmem_ld_wait();
-        issue(i + 1, rb);
+        if (i + 2 < nchunk) issue(i + 2, rb);
         drain(i, ra);
+        if (i + 2 >= nchunk) break;
         tmem_ld_wait();
-        if (i + 2 < nchunk) issue(i + 2, ra);
-        drain(i + 1, rb);
+        if (i + 4 < nchunk) issue(i + 4, ra);
+        drain(i + 2, rb);
+        if (i + 4 >= nchunk) break;
+        i += 4;
       }
       tc_fence_before();
       mbar_arrive(bar_acc_empty + 8 * buf);
@@ -416,17 +442,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 // instruction count per pixel halves.  The leader CTA (cluster rank 0) issues the MMAs; both CTAs'
 // TMA loads complete on the leader's mbarriers (cp.async.bulk.tensor ... .cta_group::2), and
 // tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs.
-constexpr int kThreads2 = 224;   // warp 0 A producer, 1 MMA, 2-5 epilogue, 6 B producer
-constexpr int kB2Stages = 6;
-constexpr uint32_t kB2StageBytes = 64 * 128;   // half of an (at most) 128-row block
-
-template <int NACC> struct Tc2Cfg {
-  static constexpr int kPatchRowsMax = NACC * kTcRowsPerAcc + 4;
-  static constexpr uint32_t kPatchBytes = kPatchRowsMax * kTcTileW * 128;
-  static constexpr int kPatchStages = NACC == 4 ? 2 : (NACC == 2 ? 3 : 4);
-  static constexpr uint32_t kSmemBytes = kPatchStages * kPatchBytes + kB2Stages * kB2StageBytes + 1024 + 256;
-};
-
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -482,17 +497,20 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, u
       : "memory");
 }
 
+
 struct Tile2 { int job, n, y0, x0, valid, nacc; };
 // Work item -> this CTA's tile.  Items [0, main_tiles) are pair-tiles (tiles 2q and 2q+1 of a job);
 // the pair-tiles of the last partial wave are handed out as NACC single-sub-tile items each.
-__device__ __forceinline__ Tile2 decode_tile2(const TcKParams& p, int item, int rank, int nacc_full) {
+template <int NACC>
+__device__ __forceinline__ Tile2 decode_tile2(const TcKParams& p, int item, int rank) {
+  using G = Geo<NACC>;
   Tile2 r;
   int pt = item, sub = 0;
-  r.nacc = nacc_full;
+  r.nacc = NACC;
   if (item >= p.main_tiles) {
     const int k = item - p.main_tiles;
-    pt = p.main_tiles + k / nacc_full;
-    sub = k - (k / nacc_full) * nacc_full;
+    pt = p.main_tiles + k / NACC;
+    sub = k - (k / NACC) * NACC;
     r.nacc = 1;
   }
   const int ppj = (p.tiles_per_job + 1) >> 1;        // pair-tiles per job
@@ -503,9 +521,9 @@ __device__ __forceinline__ Tile2 decode_tile2(const TcKParams& p, int item, int 
   const int per_frame = p.tiles_x * p.tiles_y;
   r.n = t / per_frame;
   t -= r.n * per_frame;
-  r.y0 = (t / p.tiles_x) * (nacc_full * kTcRowsPerAcc) + sub * kTcRowsPerAcc;
-  r.x0 = (t % p.tiles_x) * kTcTileW;
-  if (r.y0 >= p.H) { r.valid = 0; r.y0 = 0; }        // empty sub-tile of a split tail tile: compute, store nothing
+  r.y0 = (t / p.tiles_x) * G::TH + (sub / G::NAX) * kTcSubH;
+  r.x0 = (t % p.tiles_x) * G::TW + (sub % G::NAX) * kTcSubW;
+  if (r.y0 >= p.H || r.x0 >= p.W) { r.valid = 0; r.y0 = 0; r.x0 = 0; }   // empty sub-tile: compute, store nothing
   return r;
 }
 
@@ -514,17 +532,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap bmap0,
                 const __grid_constant__ CUtensorMap bmap1, const __grid_constant__ TcKParams p) {
   using OutT = typename OperandTraits<OPERAND>::Out;
-  using Cfg = Tc2Cfg<NACC>;
-  constexpr int NPB = Cfg::kPatchStages;
-  constexpr uint32_t ROW_BYTES = kTcTileW * 128;
+  using G = Geo<NACC>;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_patch = sbase;
-  const uint32_t s_b = sbase + NPB * Cfg::kPatchBytes;
-  const uint32_t s_bar = s_b + kB2Stages * kB2StageBytes;
-  const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * NPB;
-  const uint32_t bar_b_full = s_bar + 16 * NPB, bar_b_empty = bar_b_full + 8 * kB2Stages;
+  const uint32_t s_bar = sbase;
+  const uint32_t s_patch = sbase + kBarBytes;
+  const uint32_t s_b = s_patch + kNPB * p.patch_stage;
+  const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * kNPB;
+  const uint32_t bar_b_full = s_bar + 16 * kNPB, bar_b_empty = bar_b_full + 8 * kB2Stages;
   const uint32_t bar_acc_full = bar_b_empty + 8 * kB2Stages, bar_acc_empty = bar_acc_full + 16;
   const uint32_t s_tmem_slot = bar_acc_empty + 16;
   volatile uint32_t* tmem_slot_ptr =
@@ -535,14 +551,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   const int total_items = p.total_items;
+  const uint32_t pitch = (uint32_t)p.pw * 128u;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap1) : "memory");
-    for (int i = 0; i < NPB; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
+    for (int i = 0; i < kNPB; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
     for (int i = 0; i < kB2Stages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 512); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -557,33 +574,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ================================ A producer (both CTAs): activation patches =================
+    // ================================ A producer (both CTAs): one activation patch per slab ======
     int ps = 0;
     uint32_t pph = 0;
     const uint32_t full_leader = mapa_u32(bar_patch_full, 0);
     for (int item = cluster_id; item < total_items; item += nclusters) {
-      const Tile2 tl = decode_tile2(p, item, (int)rank, NACC);
+      const Tile2 tl = decode_tile2<NACC>(p, item, (int)rank);
       const int coff = p.job[tl.job].in_coff;
       for (int s = 0; s < p.nslab; ++s) {
-        for (int dxi = 0; dxi < p.ndx; ++dxi) {
-          mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
-          if (elect_one()) {
-            if (leader) mbar_expect_tx(bar_patch_full + 8 * ps, 2 * p.patch_tx);
-            tma_load_4d_2sm(s_patch + ps * Cfg::kPatchBytes, &tmap, full_leader + 8 * ps,
-                            coff + s * p.slab_elems, tl.x0 + p.dx_ord[dxi] - p.pad, tl.y0 - p.pad, tl.n);
-          }
-          __syncwarp();
-          if (++ps == NPB) { ps = 0; pph ^= 1; }
+        mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(bar_patch_full + 8 * ps, 2 * p.patch_tx);
+          tma_load_4d_2sm(s_patch + ps * p.patch_stage, &tmap, full_leader + 8 * ps,
+                          coff + s * p.slab_elems, tl.x0 - p.pad, tl.y0 - p.pad, tl.n);
         }
+        __syncwarp();
+        if (++ps == kNPB) { ps = 0; pph ^= 1; }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 10) {
     // ================================ B producer (both CTAs): this CTA's half of every weight block
     int bs = 0;
     uint32_t bph = 0;
     const uint32_t full_leader = mapa_u32(bar_b_full, 0);
     for (int item = cluster_id; item < total_items; item += nclusters) {
-      const Tile2 tl = decode_tile2(p, item, (int)rank, NACC);
+      const Tile2 tl = decode_tile2<NACC>(p, item, (int)rank);
       const CUtensorMap* bm = tl.job ? &bmap1 : &bmap0;
       for (int s = 0; s < p.nslab; ++s) {
         for (int dxi = 0; dxi < p.ndx; ++dxi) {
@@ -609,9 +624,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       int ps = 0, bs = 0;
       uint32_t pph = 0, bph = 0;
       int it = 0;
-      const uint64_t desc_hi = umma_desc(0);
+      const uint64_t desc_a = umma_desc_hi(pitch), desc_b = umma_desc_hi(1024);
       for (int item = cluster_id; item < total_items; item += nclusters, ++it) {
-        const Tile2 tl = decode_tile2(p, item, 0, NACC);
+        const Tile2 tl = decode_tile2<NACC>(p, item, 0);
         const int outer_col = p.job[tl.job].outer_col;
         const int buf = it % p.nbuf;
         const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
@@ -620,22 +635,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const uint32_t d_base = tmem_base + (uint32_t)(buf * NACC * p.n_cols);
         uint32_t acc0 = 0;
         for (int s = 0; s < p.nslab; ++s) {
+          mbar_wait(bar_patch_full + 8 * ps, pph);
+          const uint32_t patch = s_patch + ps * p.patch_stage;
           for (int dxi = 0; dxi < p.ndx; ++dxi) {
-            mbar_wait(bar_patch_full + 8 * ps, pph);
-            const uint32_t patch = s_patch + ps * Cfg::kPatchBytes;
             for (int dyi = 0; dyi < p.ndy; ++dyi) {
               mbar_wait(bar_b_full + 8 * bs, bph);
               tc_fence_after();
               const bool half = p.b_bytes[dxi][dyi] < (uint32_t)p.n_cols * 128u;
               const uint32_t idesc = half ? p.idesc_half : p.idesc_full;
               const uint32_t d0 = d_base + (half ? (uint32_t)outer_col : 0u);
-              const uint64_t bdesc = desc_hi | (uint64_t)(((s_b + bs * kB2StageBytes) & 0x3FFFFu) >> 4);
-              const uint64_t adesc0 = desc_hi | (uint64_t)(((patch + (uint32_t)p.dy_ord[dyi] * ROW_BYTES) & 0x3FFFFu) >> 4);
+              const uint64_t bdesc = desc_b | desc_addr(s_b + bs * kB2StageBytes);
+              const uint64_t adesc0 = desc_a | desc_addr(patch + (uint32_t)p.dy_ord[dyi] * pitch + (uint32_t)p.dx_ord[dxi] * 128u);
+              const bool last = (dxi == p.ndx - 1) && (dyi == p.ndy - 1);
               if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < NACC; ++j) {
                   if (j >= tl.nacc) break;
-                  const uint64_t adesc = adesc0 + (uint64_t)(j * kTcRowsPerAcc * (ROW_BYTES >> 4));
+                  const uint64_t adesc = adesc0 + (uint64_t)(((j / G::NAX) * kTcSubH * pitch + (j % G::NAX) * kTcSubW * 128u) >> 4);
                   const uint32_t d = d0 + (uint32_t)(j * p.n_cols);
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
@@ -644,53 +660,58 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                   }
                 }
                 umma_commit_2sm(bar_b_empty + 8 * bs);
-                if (dyi == p.ndy - 1) umma_commit_2sm(bar_patch_empty + 8 * ps);
-                if (dyi == p.ndy - 1 && dxi == p.ndx - 1 && s == p.nslab - 1) umma_commit_2sm(bar_acc_full + 8 * buf);
+                if (last) umma_commit_2sm(bar_patch_empty + 8 * ps);
+                if (last && s == p.nslab - 1) umma_commit_2sm(bar_acc_full + 8 * buf);
               }
               __syncwarp();
               acc0 = 1;
               if (++bs == kB2Stages) { bs = 0; bph ^= 1; }
             }
-            if (++ps == NPB) { ps = 0; pph ^= 1; }
           }
+          if (++ps == kNPB) { ps = 0; pph ^= 1; }
         }
       }
     }
   } else {
     // ================================ epilogue (both CTAs, own tile) ==============================
     const int q = warp & 3;
+    const int ehalf = (warp - 2) >> 2;
     const int m = q * 32 + lane;
-    const int my = m / kTcTileW, mx = m % kTcTileW;
+    const int my = m / kTcSubW, mx = m % kTcSubW;
     const uint32_t acc_empty_leader = mapa_u32(bar_acc_empty, 0);
     int it = 0;
     for (int item = cluster_id; item < total_items; item += nclusters, ++it) {
-      const Tile2 tl = decode_tile2(p, item, (int)rank, NACC);
+      const Tile2 tl = decode_tile2<NACC>(p, item, (int)rank);
       const TcJob& job = p.job[tl.job];
       const int buf = it % p.nbuf;
       mbar_wait(bar_acc_full + 8 * buf, (uint32_t)(it / p.nbuf) & 1u);
       tc_fence_after();
-      const int px = tl.x0 + mx;
       const int cpa_sh = p.n_cols == 128 ? 2 : 1, nchunk = tl.nacc << cpa_sh;    // chunks per accumulator: 4 or 2
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NACC * p.n_cols);
       auto issue = [&](int i, uint32_t (&r)[32]) { tmem_ld32(lane_base + (uint32_t)(i << 5), r); };
       auto drain = [&](int i, const uint32_t (&r)[32]) {
         const int j = i >> cpa_sh, c0 = (i - (j << cpa_sh)) << 5;
-        const int py = tl.y0 + j * kTcRowsPerAcc + my;
+        const int py = tl.y0 + (j / G::NAX) * kTcSubH + my, px = tl.x0 + (j % G::NAX) * kTcSubW + mx;
         if (tl.valid && (py < p.H) && (px < p.W)) {
           const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
           store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32);
         }
       };
+      // the two warps of a lane quarter take the even / odd chunks
       uint32_t ra[32], rb[32];
-      issue(0, ra);
+      int i = ehalf;
+      issue(i, ra);
 #pragma unroll 1
-      for (int i = 0; i < nchunk; i += 2) {
+      while (true) {
         tmem_ld_wait();
-        issue(i + 1, rb);
+        if (i + 2 < nchunk) issue(i + 2, rb);
         drain(i, ra);
+        if (i + 2 >= nchunk) break;
         tmem_ld_wait();
-        if (i + 2 < nchunk) issue(i + 2, ra);
-        drain(i + 1, rb);
+        if (i + 4 < nchunk) issue(i + 4, ra);
+        drain(i + 2, rb);
+        if (i + 4 >= nchunk) break;
+        i += 4;
       }
       tc_fence_before();
       mbar_arrive_cluster(acc_empty_leader + 8 * buf);
@@ -839,7 +860,7 @@ void tc_pack_pair_weights(const TcConvPlan& p, const float* w3, const float* w5,
 }
 
 cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, int W, int H, int B,
-                           int slab_elems, int box_rows) {
+                           int slab_elems, int box_w, int box_h) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -858,7 +879,7 @@ cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, i
                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
-  const cuuint32_t box[4] = {(cuuint32_t)slab_elems, (cuuint32_t)kTcTileW, (cuuint32_t)box_rows, 1u};
+  const cuuint32_t box[4] = {(cuuint32_t)slab_elems, (cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = encode(map, dt, 4, const_cast<void*>(base), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -889,27 +910,38 @@ cudaError_t tc_encode_bmap(CUtensorMap* map, const void* base, size_t bytes) {
 }
 
 namespace {
+// shared geometry set-up; returns the dynamic shared memory the launch needs (0 if it does not fit)
+template <int NACC>
+size_t setup_geometry(TcKParams& kp, int b_stage_bytes_total) {
+  using G = Geo<NACC>;
+  kp.tiles_x = cdiv(kp.W, G::TW);
+  kp.tiles_y = cdiv(kp.H, G::TH);
+  kp.tiles_per_job = kp.B * kp.tiles_x * kp.tiles_y;
+  kp.total_tiles = kp.tiles_per_job * kp.njobs;
+  kp.pw = G::TW + kp.ks - 1;
+  const int ph = G::TH + kp.ks - 1;
+  kp.patch_tx = (uint32_t)kp.pw * ph * 128u;
+  kp.patch_stage = (kp.patch_tx + 1023u) & ~1023u;
+  kp.nbuf = (2 * NACC * kp.n_cols <= 512) ? 2 : 1;
+  const size_t smem = 1024 + kBarBytes + (size_t)kNPB * kp.patch_stage + b_stage_bytes_total;
+  return smem <= 232448 ? smem : 0;
+}
+
 template <int NACC, int OPERAND>
 cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& b0, const CUtensorMap& b1, TcKParams& kp,
                          cudaStream_t st) {
-  using Cfg = Tc2Cfg<NACC>;
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NACC, OPERAND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NACC, OPERAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  const int tile_h = NACC * kTcRowsPerAcc;
-  kp.tiles_y = cdiv(kp.H, tile_h);
-  kp.tiles_per_job = kp.B * kp.tiles_x * kp.tiles_y;
-  kp.total_tiles = kp.tiles_per_job * kp.njobs;
-  kp.nbuf = (2 * NACC * kp.n_cols <= 512) ? 2 : 1;
-  kp.patch_tx = (uint32_t)(tile_h + kp.ks - 1) * kTcTileW * 128u;
+  const size_t smem = setup_geometry<NACC>(kp, kB2Stages * kB2StageBytes);
+  if (!smem) return cudaErrorInvalidConfiguration;
   const int items = ((kp.tiles_per_job + 1) / 2) * kp.njobs;     // pair-tiles
   int clusters = num_sms / 2;
   if (items < clusters) clusters = items;
@@ -919,28 +951,24 @@ cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& b0, const C
     kp.main_tiles = split ? items - rem : items;
     kp.total_items = kp.main_tiles + (items - kp.main_tiles) * NACC;
   }
-  conv_tc2_kernel<NACC, OPERAND><<<2 * clusters, kThreads2, Cfg::kSmemBytes, st>>>(tmap, b0, b1, kp);
+  conv_tc2_kernel<NACC, OPERAND><<<2 * clusters, kThreads2, smem, st>>>(tmap, b0, b1, kp);
   return cudaGetLastError();
 }
 
 template <int NACC, int OPERAND>
 cudaError_t launch_nacc(const CUtensorMap& tmap, TcKParams& kp, cudaStream_t st) {
-  using Cfg = TcCfg<NACC>;
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<NACC, OPERAND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<NACC, OPERAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  const int tile_h = NACC * kTcRowsPerAcc;
-  kp.tiles_y = cdiv(kp.H, tile_h);
-  kp.tiles_per_job = kp.B * kp.tiles_x * kp.tiles_y;
-  kp.total_tiles = kp.tiles_per_job * kp.njobs;
+  const size_t smem = setup_geometry<NACC>(kp, kBStages * kBStageBytes);
+  if (!smem) return cudaErrorInvalidConfiguration;
   {
     const int g = kp.total_tiles < num_sms ? kp.total_tiles : num_sms;
     const int rem = kp.total_tiles % g;
@@ -949,10 +977,8 @@ cudaError_t launch_nacc(const CUtensorMap& tmap, TcKParams& kp, cudaStream_t st)
     kp.main_tiles = split ? kp.total_tiles - rem : kp.total_tiles;
     kp.total_items = kp.main_tiles + (kp.total_tiles - kp.main_tiles) * NACC;
   }
-  kp.nbuf = (2 * NACC * kp.n_cols <= 512) ? 2 : 1;
-  kp.patch_tx = (uint32_t)(tile_h + kp.ks - 1) * kTcTileW * 128u;
   const int grid = kp.total_tiles < num_sms ? kp.total_tiles : num_sms;
-  conv_tc_kernel<NACC, OPERAND><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmap, kp);
+  conv_tc_kernel<NACC, OPERAND><<<grid, kThreads, smem, st>>>(tmap, kp);
   return cudaGetLastError();
 }
 }  // namespace
@@ -962,7 +988,6 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const TcConvPlan& plan, cons
   memset(&kp, 0, sizeof(kp));
   for (int i = 0; i < L.njobs; ++i) kp.job[i] = L.job[i];
   kp.njobs = L.njobs; kp.B = L.B; kp.H = L.H; kp.W = L.W;
-  kp.tiles_x = cdiv(L.W, kTcTileW);
   kp.nslab = plan.nslab; kp.slab_elems = plan.slab_elems; kp.ks = plan.ks; kp.pad = plan.ks / 2;
   kp.ndx = plan.ndx; kp.ndy = plan.ndy;
   for (int i = 0; i < kTcMaxTaps; ++i) { kp.dx_ord[i] = plan.dx_ord[i]; kp.dy_ord[i] = plan.dy_ord[i]; }

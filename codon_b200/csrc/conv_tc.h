@@ -7,8 +7,8 @@
 
 namespace codon {
 
-constexpr int kTcTileW = 16;          // tile width in pixels: one patch row = 16 px * 128 B = 2 KB
-constexpr int kTcRowsPerAcc = 8;      // 128 / kTcTileW image rows per 128-row accumulator
+constexpr int kTcSubW = 8;            // an accumulator (128 GEMM rows) covers a sub-tile of 8 x 16 pixels
+constexpr int kTcSubH = 16;
 constexpr int kTcMaxTaps = 5;
 
 enum TcOperand : int { TC_F16 = 0, TC_BF16 = 1, TC_TF32 = 2 };   // == UMMA F16F32Format
@@ -64,12 +64,16 @@ struct TcLaunch {
   const CUtensorMap* bmap[2] = {nullptr, nullptr};   // per job: 2-D map of the packed weight stream
 };
 
-// Box height (image rows) the A tensor map must be encoded with for this plan / nacc.
-inline int tc_box_rows(const TcConvPlan& p, int nacc) { return nacc * kTcRowsPerAcc + p.ks - 1; }
+// Tile geometry for `nacc` accumulators: NAX x NAY sub-tiles (1x1, 2x1, 2x2).
+inline int tc_tile_w(int nacc) { return (nacc >= 2 ? 2 : 1) * kTcSubW; }
+inline int tc_tile_h(int nacc) { return (nacc >= 4 ? 2 : 1) * kTcSubH; }
+// Patch box (pixels, rows) the A tensor map must be encoded with for this plan / nacc.
+inline int tc_box_w(const TcConvPlan& p, int nacc) { return tc_tile_w(nacc) + p.ks - 1; }
+inline int tc_box_h(const TcConvPlan& p, int nacc) { return tc_tile_h(nacc) + p.ks - 1; }
 
-// Encodes the 4-D NHWC tensor map {C, W, H, B} with box {slab_elems, 16, box_rows, 1}, SWIZZLE_128B.
+// Encodes the 4-D NHWC tensor map {C, W, H, B} with box {slab_elems, box_w, box_h, 1}, SWIZZLE_128B.
 cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, int W, int H, int B,
-                           int slab_elems, int box_rows);
+                           int slab_elems, int box_w, int box_h);
 
 // 2-D tensor map over a packed weight stream (rows of 128 B, 32-row boxes) for the 2-CTA kernel.
 cudaError_t tc_encode_bmap(CUtensorMap* map, const void* base, size_t bytes);
