@@ -159,7 +159,7 @@ Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W) {
   b.E = take(P * 128 * e); b.F = take(P * 128 * e);
   b.MS = take(P * 256 * e); b.R2 = take(P * 256 * e);
   b.FUSE = take(P * 64 * e); b.OF = take(P * 64 * e);
-  b.pooled = take(P * 2 * 4);
+  b.pooled = take(P * 2 * 4 * 2);   // (max, mean) map, or two per-branch (max, sum) partial maps
   b.chunks = cac_stats_chunks(B, H, W);
   b.part = take((size_t)B * b.chunks * 256 * 4);
   b.sc = take((size_t)B * 64 * 4);
@@ -234,7 +234,7 @@ int use_two_cta(int B, int H, int W, int nacc) {
 }
 
 // One conv layer of the plan: up to two jobs reading channel slices of `in` (in_C channels).
-struct LayerJob { const char* w; int in_off; size_t out; int out_stride, out_off; size_t res; int res_stride, res_off; bool has_res; };
+struct LayerJob { const char* w; int in_off; size_t out; int out_stride, out_off; size_t res; int res_stride, res_off; bool has_res; size_t pool = 0; bool has_pool = false; };
 
 struct Runner {
   codon_ctx* ctx; uint8_t* ws; int B, H, W; cudaStream_t st; int e;
@@ -269,6 +269,7 @@ struct Runner {
       L.job[i].res = jobs[i].has_res ? ws + jobs[i].res : nullptr;
       L.job[i].res_stride = jobs[i].res_stride; L.job[i].res_off = jobs[i].res_off;
       L.job[i].outer_col = 0;
+      L.job[i].pool = jobs[i].has_pool ? reinterpret_cast<float2*>(ws + jobs[i].pool) : nullptr;
       L.bmap[i] = &l.bmap;
     }
     // the HBM-bound 1x1 / 3x3 layers measured slower in cluster mode; the 5x5 layers gain 15-20 %
@@ -315,6 +316,7 @@ struct Runner {
       L.job[i].out = ws + out; L.job[i].out_stride = out_stride; L.job[i].out_off = out_off[i];
       L.job[i].res = nullptr; L.job[i].res_stride = 0; L.job[i].res_off = 0;
       L.job[i].outer_col = three_first[i] ? 64 : 0;
+      L.job[i].pool = nullptr;
       L.bmap[i] = &l.bmap;
     }
     L.two_cta = use_two_cta(B, H, W, L.nacc);
@@ -331,6 +333,7 @@ struct Runner {
 int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int B, int H, int W, uint8_t* ws,
                 const Buffers& bf, cudaStream_t st) {
   Runner r{ctx, ws, B, H, W, st, act_bytes(ctx->act)};
+  const bool tc_mode = ctx->mode != CODON_MODE_FP32;
   int rc;
   // encoders (CODON_x4.py:68-73): input/input_c 1->64 (+ReLU) into the R2 region viewed as 128 ch
   const size_t T0 = bf.R2;
@@ -360,6 +363,10 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     }
     {
       LayerJob j[2] = {{"confuse", 0, bf.F, 128, 0, 0, 0, 0, false}, {"confuse_c", 128, bf.F, 128, 64, 0, 0, 0, false}};
+      if (tc_mode) {   // the 1x1 epilogues emit the per-branch ChannelPool partials (max, sum) per pixel
+        j[0].pool = bf.pooled; j[0].has_pool = true;
+        j[1].pool = bf.pooled + (size_t)B * H * W * 8; j[1].has_pool = true;
+      }
       if ((rc = r.conv("", bf.R2, 256, 128, 64, 1, false, j, 2))) return rc;
     }
     // CAC gates (:85-118, CAC_module.py:38-63, 78-94)
@@ -369,7 +376,8 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     // algorithmic HBM bytes: stats reads F (128e B/px); apply reads F and E, writes F (384e B/px)
     {
       ProfScope ps(ctx, PC_CAC_STATS, P * 128 * r.e, st);
-      CU_TRY(ctx, launch_cac_stats(ws + bf.F, ctx->act, B, H, W, pooled, part, bf.chunks, st));
+      if (tc_mode) CU_TRY(ctx, launch_cac_chan_stats(ws + bf.F, ctx->act, B, H, W, part, bf.chunks, st));
+      else CU_TRY(ctx, launch_cac_stats(ws + bf.F, ctx->act, B, H, W, pooled, part, bf.chunks, st));
     }
     {
       ProfScope ps(ctx, PC_CAC_MLP, 0.0, st);
@@ -378,7 +386,7 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     }
     {
       ProfScope ps(ctx, PC_CAC_APPLY, P * 384 * r.e, st);
-      CU_TRY(ctx, launch_cac_apply(ws + bf.F, ws + bf.E, ctx->act, pooled, sc, ctx->cac_ws[s], B, H, W, st, ctx->mode == CODON_MODE_TF32));
+      CU_TRY(ctx, launch_cac_apply(ws + bf.F, ws + bf.E, ctx->act, pooled, sc, ctx->cac_ws[s], B, H, W, st, ctx->mode == CODON_MODE_TF32, tc_mode ? 2 : 1));
     }
     ctx->launches += 3;
   }

@@ -91,6 +91,94 @@ __global__ void __launch_bounds__(256, 4) cac_stats_kernel(const T* __restrict__
   }
 }
 
+// Lean variant for the tensor-core modes: the per-pixel ChannelPool partials are emitted by the producing
+// 1x1 convolution's epilogue (conv_tc.cu, TcJob::pool), so this kernel only accumulates the per-channel
+// sum / max of its 256-pixel chunk: no cross-lane work in the loop, the max runs on packed 16-bit pairs.
+template <typename T> struct PackedMax;
+template <> struct PackedMax<float> {
+  using Acc = uint4;
+  __device__ static inline uint4 init() { const uint32_t n = 0xff800000u; return make_uint4(n, n, n, n); }
+  __device__ static inline void upd(uint4& a, const uint4& v) {
+    a.x = __float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(v.x)));
+    a.y = __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(v.y)));
+    a.z = __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(v.z)));
+    a.w = __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(v.w)));
+  }
+};
+template <> struct PackedMax<__nv_bfloat16> {
+  __device__ static inline uint4 init() { const uint32_t n = 0xff80ff80u; return make_uint4(n, n, n, n); }
+  __device__ static inline uint32_t mx(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __device__ static inline void upd(uint4& a, const uint4& v) { a.x = mx(a.x, v.x); a.y = mx(a.y, v.y); a.z = mx(a.z, v.z); a.w = mx(a.w, v.w); }
+};
+template <> struct PackedMax<__half> {
+  __device__ static inline uint4 init() { const uint32_t n = 0xfc00fc00u; return make_uint4(n, n, n, n); }
+  __device__ static inline uint32_t mx(uint32_t a, uint32_t b) {
+    __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __device__ static inline void upd(uint4& a, const uint4& v) { a.x = mx(a.x, v.x); a.y = mx(a.y, v.y); a.z = mx(a.z, v.z); a.w = mx(a.w, v.w); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256, 4) cac_chan_stats_kernel(const T* __restrict__ F, int HW, int chunks,
+                                                                float* __restrict__ part) {
+  constexpr int V = Act<T>::kVec, LPP = 128 / V, PPW = 32 / LPP, kU = 8;
+  constexpr int ROWPX = 8 * PPW;
+  constexpr int NIT = kChunkPx / (ROWPX * kU);
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane % LPP, sub = lane / LPP;
+  const int p_begin = chunk * kChunkPx, p_end = min(p_begin + kChunkPx, HW);
+  const T* base = F + (size_t)b * HW * 128;
+
+  float csum[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) csum[j] = 0.f;
+  uint4 cmax = PackedMax<T>::init();
+
+#pragma unroll 1
+  for (int it = 0; it < NIT; ++it) {
+    const int p0 = p_begin + it * ROWPX * kU + warp * PPW + sub;
+    uint4 raw[kU];
+    bool ok[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int p = p0 + u * ROWPX;
+      ok[u] = p < p_end;
+      if (ok[u]) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * 128 + g * V));
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (ok[u]) {
+        float v[V];
+        Act<T>::unpack(raw[u], v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) csum[j] += v[j];
+        PackedMax<T>::upd(cmax, raw[u]);
+      }
+    }
+  }
+  float cmx[V];
+  Act<T>::unpack(cmax, cmx);
+  __shared__ float rs[8 * PPW][128], rm[8 * PPW][128];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    rs[warp * PPW + sub][g * V + j] = csum[j];
+    rm[warp * PPW + sub][g * V + j] = cmx[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float s = 0.f, m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 8 * PPW; ++r) { s += rs[r][threadIdx.x]; m = fmaxf(m, rm[r][threadIdx.x]); }
+    float* dst = part + ((size_t)(b * chunks + chunk) * 2) * 128;
+    dst[threadIdx.x] = s;
+    dst[128 + threadIdx.x] = m;
+  }
+}
+
 // One CTA per frame, 1024 threads.  F channel c (depth 0..63 | colour 64..127) is Fcat channel
 // (c + 64) % 128 (Fcat = [colour | depth], CODON_x4.py:85); w1 is indexed by Fcat channel.
 // The chunk partials are reduced in a fixed order (4 interleaved lanes per column, then a fixed
@@ -156,7 +244,7 @@ __global__ void __launch_bounds__(256) cac_apply_kernel(T* __restrict__ F, const
                                                         const float* __restrict__ pooled,
                                                         const float* __restrict__ sc,
                                                         const float* __restrict__ ws, int H, int W,
-                                                        int tiles_x, int rnd_tf32) {
+                                                        int tiles_x, int rnd_tf32, int pool_parts, size_t part_stride) {
   constexpr int V = Act<T>::kVec, LPP = 128 / V, PH = kATH + 4, PW = kATW + 4;
   __shared__ float2 sp[PH][PW];
   __shared__ float sw[50], ssc[64], sss[kATH * kATW];
@@ -168,8 +256,14 @@ __global__ void __launch_bounds__(256) cac_apply_kernel(T* __restrict__ F, const
   for (int i = t; i < PH * PW; i += 256) {
     const int gy = ty0 + i / PW - 2, gx = tx0 + i % PW - 2;
     float2 v = make_float2(0.f, 0.f);
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
       v = __ldg(reinterpret_cast<const float2*>(pooled + (fb + (size_t)gy * W + gx) * 2));
+      if (pool_parts == 2) {
+        // two per-branch (max, sum) partials from the 1x1 conv epilogues -> (max, mean) over the 128 channels
+        const float2 w = __ldg(reinterpret_cast<const float2*>(pooled + (part_stride + fb + (size_t)gy * W + gx) * 2));
+        v = make_float2(fmaxf(v.x, w.x), (v.y + w.y) * (1.0f / 128.0f));
+      }
+    }
     sp[i / PW][i % PW] = v;
   }
   __syncthreads();
@@ -223,6 +317,16 @@ cudaError_t launch_cac_stats(const void* F, int act, int B, int H, int W, float*
   return cudaGetLastError();
 }
 
+cudaError_t launch_cac_chan_stats(const void* F, int act, int B, int H, int W, float* part, int chunks,
+                                  cudaStream_t st) {
+  dim3 grid(chunks, B);
+  const int HW = H * W;
+  if (act == ACT_F32) cac_chan_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)F, HW, chunks, part);
+  else if (act == ACT_BF16) cac_chan_stats_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)F, HW, chunks, part);
+  else cac_chan_stats_kernel<__half><<<grid, 256, 0, st>>>((const __half*)F, HW, chunks, part);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const float* w1, const float* b1,
                            const float* w2, const float* b2, float* sc, cudaStream_t st) {
   cac_mlp_kernel<<<B, 1024, 0, st>>>(part, chunks, HW, w1, b1, w2, b2, sc);
@@ -230,12 +334,13 @@ cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const f
 }
 
 cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* pooled, const float* sc,
-                             const float* ws, int B, int H, int W, cudaStream_t st, int rnd_tf32) {
+                             const float* ws, int B, int H, int W, cudaStream_t st, int rnd_tf32, int pool_parts) {
   const int tiles_x = cdiv(W, kATW);
+  const size_t part_stride = (size_t)B * H * W;
   dim3 grid(tiles_x * cdiv(H, kATH), B);
-  if (act == ACT_F32) cac_apply_kernel<float><<<grid, 256, 0, st>>>((float*)F, (const float*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32);
-  else if (act == ACT_BF16) cac_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)F, (const __nv_bfloat16*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32);
-  else cac_apply_kernel<__half><<<grid, 256, 0, st>>>((__half*)F, (const __half*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32);
+  if (act == ACT_F32) cac_apply_kernel<float><<<grid, 256, 0, st>>>((float*)F, (const float*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride);
+  else if (act == ACT_BF16) cac_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)F, (const __nv_bfloat16*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride);
+  else cac_apply_kernel<__half><<<grid, 256, 0, st>>>((__half*)F, (const __half*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride);
   return cudaGetLastError();
 }
 

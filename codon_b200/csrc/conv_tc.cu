@@ -38,7 +38,7 @@ namespace codon {
 
 namespace {
 
-constexpr int kNPB = 2;                        // patch stages
+constexpr int kMaxNPB = 8;                     // patch stages: as many as fit (runtime, TcKParams::npb)
 constexpr int kBStages = 4;
 constexpr uint32_t kBStageBytes = 128 * 128;   // up to 128 rows x 128 B
 constexpr int kThreads = 320;                  // warp 0 producer, 1 MMA, 2-9 epilogue (two warps per TMEM lane quarter)
@@ -60,6 +60,7 @@ struct TcKParams {
   int relu, out_act, is_tf32, nbuf;
   int pw;                        // patch width in pixels (tile_w + ks - 1); the patch row pitch is pw * 128 B
   uint32_t patch_tx, patch_stage;   // bytes of one patch (TMA transaction) and of one patch stage (1024-aligned)
+  int npb;                       // patch stages in the ring (2 .. kMaxNPB)
   int debug;   // CODON_TC_DEBUG bits (perf experiments only, 1-CTA kernel): 1 no epilogue stores, 2 no B loads, 4 no A loads, 8 no MMAs, 16 no waits
 };
 
@@ -250,10 +251,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_bar = sbase;
   const uint32_t s_patch = sbase + kBarBytes;
-  const uint32_t s_b = s_patch + kNPB * p.patch_stage;
+  const uint32_t s_b = s_patch + p.npb * p.patch_stage;
   // barrier map (8 B each)
-  const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * kNPB;
-  const uint32_t bar_b_full = s_bar + 16 * kNPB, bar_b_empty = bar_b_full + 8 * kBStages;
+  const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * kMaxNPB;
+  const uint32_t bar_b_full = s_bar + 16 * kMaxNPB, bar_b_empty = bar_b_full + 8 * kBStages;
   const uint32_t bar_acc_full = bar_b_empty + 8 * kBStages, bar_acc_empty = bar_acc_full + 16;
   const uint32_t s_tmem_slot = bar_acc_empty + 16;
   volatile uint32_t* tmem_slot_ptr =
@@ -264,7 +265,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-    for (int i = 0; i < kNPB; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
+    for (int i = 0; i < p.npb; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
     for (int i = 0; i < kBStages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -299,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           }
         }
         __syncwarp();
-        if (++ps == kNPB) { ps = 0; pph ^= 1; }
+        if (++ps == p.npb) { ps = 0; pph ^= 1; }
         for (int dxi = 0; dxi < p.ndx; ++dxi) {
           for (int dyi = 0; dyi < p.ndy; ++dyi) {
             mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
@@ -372,7 +373,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             if (++bs == kBStages) { bs = 0; bph ^= 1; }
           }
         }
-        if (++ps == kNPB) { ps = 0; pph ^= 1; }
+        if (++ps == p.npb) { ps = 0; pph ^= 1; }
       }
       ++it;
     }
@@ -396,29 +397,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const int cpa_sh = p.n_cols == 128 ? 2 : 1, nchunk = tl.nacc << cpa_sh;    // chunks per accumulator: 4 or 2
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NACC * p.n_cols);
       auto issue = [&](int i, uint32_t (&r)[32]) { tmem_ld32(lane_base + (uint32_t)(i << 5), r); };
+      const bool pool_mode = job.pool != nullptr;           // 64-column launches only (host-checked)
+      float pmax = -INFINITY, psum = 0.f;
       auto drain = [&](int i, const uint32_t (&r)[32]) {
         const int j = i >> cpa_sh, c0 = (i - (j << cpa_sh)) << 5;
         const int py = tl.y0 + (j / G::NAX) * kTcSubH + my, px = tl.x0 + (j % G::NAX) * kTcSubW + mx;
         if ((py < p.H) && (px < p.W) && !(p.debug & 1)) {
           const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
           store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32);
+          if (pool_mode) {
+            // ChannelPool partial over this job's 64 channels (the thread sees both 32-column chunks of its pixel)
+            float m = __uint_as_float(r[0]), sacc = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) { const float v = __uint_as_float(r[e]); m = fmaxf(m, v); sacc += v; }
+            if (c0 == 0) { pmax = m; psum = sacc; }
+            else job.pool[pix] = make_float2(fmaxf(pmax, m), psum + sacc);
+          }
         }
       };
-      // the two warps of a lane quarter take the even / odd chunks
+      // Chunk schedule of this warp.  Normally the two warps of a lane quarter take the even / odd chunks;
+      // in pool mode they take alternate accumulators (both chunks), so a thread owns all 64 channels.
+      auto nxt = [&](int i) { return pool_mode ? ((i & 1) ? i + 3 : i + 1) : i + 2; };
       uint32_t ra[32], rb[32];
-      int i = ehalf;
-      issue(i, ra);
+      int i = pool_mode ? 2 * ehalf : ehalf;
+      if (i < nchunk) {
+        issue(i, ra);
 #pragma unroll 1
-      while (true) {
-        tmem_ld_wait();
-        if (i + 2 < nchunk) issue(i + 2, rb);
-        drain(i, ra);
-        if (i + 2 >= nchunk) break;
-        tmem_ld_wait();
-        if (i + 4 < nchunk) issue(i + 4, ra);
-        drain(i + 2, rb);
-        if (i + 4 >= nchunk) break;
-        i += 4;
+        while (true) {
+          tmem_ld_wait();
+          const int i1 = nxt(i);
+          if (i1 < nchunk) issue(i1, rb);
+          drain(i, ra);
+          if (i1 >= nchunk) break;
+          tmem_ld_wait();
+          const int i2 = nxt(i1);
+          if (i2 < nchunk) issue(i2, ra);
+          drain(i1, rb);
+          if (i2 >= nchunk) break;
+          i = i2;
+        }
       }
       tc_fence_before();
       mbar_arrive(bar_acc_empty + 8 * buf);
@@ -538,9 +555,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_bar = sbase;
   const uint32_t s_patch = sbase + kBarBytes;
-  const uint32_t s_b = s_patch + kNPB * p.patch_stage;
-  const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * kNPB;
-  const uint32_t bar_b_full = s_bar + 16 * kNPB, bar_b_empty = bar_b_full + 8 * kB2Stages;
+  const uint32_t s_b = s_patch + p.npb * p.patch_stage;
+  const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * kMaxNPB;
+  const uint32_t bar_b_full = s_bar + 16 * kMaxNPB, bar_b_empty = bar_b_full + 8 * kB2Stages;
   const uint32_t bar_acc_full = bar_b_empty + 8 * kB2Stages, bar_acc_empty = bar_acc_full + 16;
   const uint32_t s_tmem_slot = bar_acc_empty + 16;
   volatile uint32_t* tmem_slot_ptr =
@@ -557,7 +574,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap1) : "memory");
-    for (int i = 0; i < kNPB; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
+    for (int i = 0; i < p.npb; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
     for (int i = 0; i < kB2Stages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 512); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -589,7 +606,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                           coff + s * p.slab_elems, tl.x0 - p.pad, tl.y0 - p.pad, tl.n);
         }
         __syncwarp();
-        if (++ps == kNPB) { ps = 0; pph ^= 1; }
+        if (++ps == p.npb) { ps = 0; pph ^= 1; }
       }
     }
   } else if (warp == 10) {
@@ -668,7 +685,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
               if (++bs == kB2Stages) { bs = 0; bph ^= 1; }
             }
           }
-          if (++ps == kNPB) { ps = 0; pph ^= 1; }
+          if (++ps == p.npb) { ps = 0; pph ^= 1; }
         }
       }
     }
@@ -923,8 +940,12 @@ size_t setup_geometry(TcKParams& kp, int b_stage_bytes_total) {
   kp.patch_tx = (uint32_t)kp.pw * ph * 128u;
   kp.patch_stage = (kp.patch_tx + 1023u) & ~1023u;
   kp.nbuf = (2 * NACC * kp.n_cols <= 512) ? 2 : 1;
-  const size_t smem = 1024 + kBarBytes + (size_t)kNPB * kp.patch_stage + b_stage_bytes_total;
-  return smem <= 232448 ? smem : 0;
+  const size_t fixed = 1024 + kBarBytes + (size_t)b_stage_bytes_total;
+  int npb = (int)((232448 - fixed) / kp.patch_stage);
+  if (npb > kMaxNPB) npb = kMaxNPB;
+  if (npb < 2) return 0;
+  kp.npb = npb;
+  return fixed + (size_t)npb * kp.patch_stage;
 }
 
 template <int NACC, int OPERAND>
@@ -1006,6 +1027,8 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const TcConvPlan& plan, cons
   }
   if (L.out_act != (plan.operand == TC_TF32 ? ACT_F32 : plan.operand == TC_BF16 ? ACT_BF16 : ACT_F16))
     return cudaErrorInvalidValue;   // activations are stored in the operand type
+  for (int i = 0; i < L.njobs; ++i)
+    if (L.job[i].pool && (plan.n_cols != 64 || L.two_cta)) return cudaErrorInvalidValue;
   if (L.two_cta) {
     if (!L.bmap[0] || (L.njobs > 1 && !L.bmap[1])) return cudaErrorInvalidValue;
     const CUtensorMap& b0 = *L.bmap[0];

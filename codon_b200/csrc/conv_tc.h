@@ -51,6 +51,8 @@ struct TcJob {
   void* out;       int out_stride; int out_off;   // elements
   const void* res; int res_stride; int res_off;
   int outer_col;               // pair plans: accumulator column of the 5x5-only (outer) taps
+  float2* pool;                // optional (64-column launches, 1-CTA kernel): per-pixel (max, sum) over this job's
+                               // 64 output channels -> pool[pixel]; the CAC ChannelPool partial (CAC_module.py:78-81)
 };
 
 struct TcLaunch {

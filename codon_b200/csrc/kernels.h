@@ -38,6 +38,10 @@ cudaError_t launch_conv_last(const void* in, int in_stride, int act, const float
 int cac_stats_chunks(int B, int H, int W);
 cudaError_t launch_cac_stats(const void* F, int act, int B, int H, int W, float* pooled,
                              float* part, int chunks, cudaStream_t st);
+// lean stats (tensor-core modes): per-chunk per-channel (sum, max) only; the per-pixel ChannelPool partials
+// come from the 1x1 conv epilogues (two [B,H,W] float2 arrays, one per branch: (max, sum) over 64 channels).
+cudaError_t launch_cac_chan_stats(const void* F, int act, int B, int H, int W, float* part, int chunks,
+                                  cudaStream_t st);
 // mlp: deterministic reduce of the partials, MLP 128->8->64 on avg and max, sigmoid -> sc [B,64].
 // w1 [8][128] indexed by Fcat channel (colour | depth, CODON_x4.py:85), b1 [8], w2 [64][8], b2 [64].
 cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const float* w1,
@@ -46,7 +50,8 @@ cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const f
 // apply: F = F * sc[b, c % 64] * sigmoid(conv5x5(pooled))[b,h,w] + E   (in place on F).
 // ws fp32 [2][25] (max map taps, then mean map taps).
 cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* pooled, const float* sc,
-                             const float* ws, int B, int H, int W, cudaStream_t st, int rnd_tf32 = 0);
+                             const float* ws, int B, int H, int W, cudaStream_t st, int rnd_tf32 = 0,
+                             int pool_parts = 1);   // 1: pooled = final (max, mean) [B,H,W,2]; 2: two (max, sum) partial maps
 
 // ---- utility -------------------------------------------------------------------------------------
 cudaError_t launch_convert_to_f32(const void* src, int dtype, float* dst, size_t n, cudaStream_t st);
