@@ -7,8 +7,9 @@
 //
 //   E    128 ch  [enc_d | enc_c]      encoder outputs = residual carriers of the 5 stages (:70,73)
 //   F    128 ch  [out_d | out_c]      stage outputs; conv7 reads it as cat(out, out_c) (:119)
-//   MS   256 ch  [ms_d | ms_c]        multi-scale pairs: depth [3x3|5x5] (:79), colour [5x5|3x3] (:80)
-//   R2   256 ch  [r2_d | r2_c]        conv3 / conv6 outputs (:81-82)
+//   MS   2 x 128 ch  ms_d, ms_c       multi-scale pairs: depth [3x3|5x5] (:79), colour [5x5|3x3] (:80); one
+//                                     128-channel buffer per branch (depth first, colour P*128 elements later)
+//   R2   2 x 128 ch  r2_d, r2_c       conv3 / conv6 outputs (:81-82), same split
 //   FUSE  64 ch  conv7 output = residual carrier of the fusion stages (:120-121)
 //   OF    64 ch  out_fuse (:127-128)
 //
@@ -234,7 +235,7 @@ int use_two_cta(int B, int H, int W, int nacc) {
 }
 
 // One conv layer of the plan: up to two jobs reading channel slices of `in` (in_C channels).
-struct LayerJob { const char* w; int in_off; size_t out; int out_stride, out_off; size_t res; int res_stride, res_off; bool has_res; size_t pool = 0; bool has_pool = false; };
+struct LayerJob { const char* w; int in_off; size_t out; int out_stride, out_off; size_t res; int res_stride, res_off; bool has_res; size_t pool = 0; bool has_pool = false; size_t in_add = 0; };
 
 struct Runner {
   codon_ctx* ctx; uint8_t* ws; int B, H, W; cudaStream_t st; int e;
@@ -245,7 +246,7 @@ struct Runner {
     if (ctx->mode == CODON_MODE_FP32) {
       ConvJob cj[2];
       for (int i = 0; i < njobs; ++i) {
-        cj[i].in = ws + in; cj[i].in_stride = in_C; cj[i].in_off = jobs[i].in_off;
+        cj[i].in = ws + in + jobs[i].in_add; cj[i].in_stride = in_C; cj[i].in_off = jobs[i].in_off;
         cj[i].w = ctx->w_direct.at(jobs[i].w);
         cj[i].out = ws + jobs[i].out; cj[i].out_stride = jobs[i].out_stride; cj[i].out_off = jobs[i].out_off;
         cj[i].res = jobs[i].has_res ? ws + jobs[i].res : nullptr;
@@ -274,11 +275,14 @@ struct Runner {
     }
     // the HBM-bound 1x1 / 3x3 layers measured slower in cluster mode; the 5x5 layers gain 15-20 %
     L.two_cta = ks == 5 ? use_two_cta(B, H, W, L.nacc) : 0;
-    const CUtensorMap* tm = nullptr;
-    int rc = get_tmap(ctx, ws + in, in_C, tc_box_w(l0.plan, L.nacc), tc_box_h(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
-    if (rc) return rc;
+    const CUtensorMap* tm[2] = {nullptr, nullptr};
+    for (int i = 0; i < njobs; ++i) {
+      int rc = get_tmap(ctx, ws + in + jobs[i].in_add, in_C, tc_box_w(l0.plan, L.nacc), tc_box_h(l0.plan, L.nacc),
+                        l0.plan.slab_elems, B, H, W, &tm[i]);
+      if (rc) return rc;
+    }
     ProfScope ps(ctx, cat_of(cin, cout, ks), flops, st);
-    CU_TRY(ctx, launch_conv_tc(*tm, l0.plan, L, st));
+    CU_TRY(ctx, launch_conv_tc(*tm[0], *tm[njobs - 1], l0.plan, L, st));
     ctx->launches++;
     return CODON_OK;
   }
@@ -294,12 +298,12 @@ struct Runner {
   // three_first[i]: job i writes [3x3 | 5x5] (depth branch) else [5x5 | 3x3].
   int pair(size_t in, int in_C, const int* in_off, const char* const* w3, const char* const* w5,
            const char* const* wpair, const bool* three_first, size_t out, int out_stride, const int* out_off,
-           int njobs) {
+           const size_t* out_add, int njobs) {
     if (ctx->mode == CODON_MODE_FP32) {
       LayerJob j3[2], j5[2];
       for (int i = 0; i < njobs; ++i) {
-        j3[i] = {w3[i], in_off[i], out, out_stride, out_off[i] + (three_first[i] ? 0 : 64), 0, 0, 0, false};
-        j5[i] = {w5[i], in_off[i], out, out_stride, out_off[i] + (three_first[i] ? 64 : 0), 0, 0, 0, false};
+        j3[i] = {w3[i], in_off[i], out + out_add[i], out_stride, out_off[i] + (three_first[i] ? 0 : 64), 0, 0, 0, false};
+        j5[i] = {w5[i], in_off[i], out + out_add[i], out_stride, out_off[i] + (three_first[i] ? 64 : 0), 0, 0, 0, false};
       }
       int rc = conv("", in, in_C, 64, 64, 3, true, j3, njobs);
       if (rc) return rc;
@@ -313,7 +317,7 @@ struct Runner {
       const TcLayer& l = ctx->w_tc.at(wpair[i]);
       L.job[i].in_coff = in_off[i];
       L.job[i].w = l.dev;
-      L.job[i].out = ws + out; L.job[i].out_stride = out_stride; L.job[i].out_off = out_off[i];
+      L.job[i].out = ws + out + out_add[i]; L.job[i].out_stride = out_stride; L.job[i].out_off = out_off[i];
       L.job[i].res = nullptr; L.job[i].res_stride = 0; L.job[i].res_off = 0;
       L.job[i].outer_col = three_first[i] ? 64 : 0;
       L.job[i].pool = nullptr;
@@ -324,7 +328,7 @@ struct Runner {
     int rc = get_tmap(ctx, ws + in, in_C, tc_box_w(l0.plan, L.nacc), tc_box_h(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
     if (rc) return rc;
     ProfScope ps(ctx, PC_PAIR, 2.0 * B * H * W * 64.0 * 64.0 * 34.0 * njobs, st);
-    CU_TRY(ctx, launch_conv_tc(*tm, l0.plan, L, st));
+    CU_TRY(ctx, launch_conv_tc(*tm, *tm, l0.plan, L, st));
     ctx->launches++;
     return CODON_OK;
   }
@@ -334,6 +338,9 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
                 const Buffers& bf, cudaStream_t st) {
   Runner r{ctx, ws, B, H, W, st, act_bytes(ctx->act)};
   const bool tc_mode = ctx->mode != CODON_MODE_FP32;
+  // MS and R2 hold the depth branch in their first half and the colour branch in the second (128 channels
+  // each, pixel-contiguous per branch: a branch's 256/512-byte pixel rows are read and written whole)
+  const size_t half = (size_t)B * H * W * 128 * r.e;
   int rc;
   // encoders (CODON_x4.py:68-73): input/input_c 1->64 (+ReLU) into the R2 region viewed as 128 ch
   const size_t T0 = bf.R2;
@@ -351,23 +358,26 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
   for (int s = 0; s < 5; ++s) {
     const size_t src = s == 0 ? bf.E : bf.F;
     {
-      const int in_off[2] = {0, 64}, out_off[2] = {0, 128};
+      const int in_off[2] = {0, 64}, out_off[2] = {0, 0};
+      const size_t out_add[2] = {0, half};
       const char* w3[2] = {"conv1", "conv5"}; const char* w5[2] = {"conv2", "conv4"};
       const char* wp[2] = {"pair_d", "pair_c"};
       const bool tf[2] = {true, false};
-      if ((rc = r.pair(src, 128, in_off, w3, w5, wp, tf, bf.MS, 256, out_off, 2))) return rc;
+      if ((rc = r.pair(src, 128, in_off, w3, w5, wp, tf, bf.MS, 128, out_off, out_add, 2))) return rc;
     }
     {
-      LayerJob j[2] = {{"conv3", 0, bf.R2, 256, 0, 0, 0, 0, false}, {"conv6", 128, bf.R2, 256, 128, 0, 0, 0, false}};
-      if ((rc = r.conv("", bf.MS, 256, 128, 128, 5, true, j, 2))) return rc;
+      LayerJob j[2] = {{"conv3", 0, bf.R2, 128, 0, 0, 0, 0, false}, {"conv6", 0, bf.R2 + half, 128, 0, 0, 0, 0, false}};
+      j[1].in_add = half;
+      if ((rc = r.conv("", bf.MS, 128, 128, 128, 5, true, j, 2))) return rc;
     }
     {
-      LayerJob j[2] = {{"confuse", 0, bf.F, 128, 0, 0, 0, 0, false}, {"confuse_c", 128, bf.F, 128, 64, 0, 0, 0, false}};
+      LayerJob j[2] = {{"confuse", 0, bf.F, 128, 0, 0, 0, 0, false}, {"confuse_c", 0, bf.F, 128, 64, 0, 0, 0, false}};
+      j[1].in_add = half;
       if (tc_mode) {   // the 1x1 epilogues emit the per-branch ChannelPool partials (max, sum) per pixel
         j[0].pool = bf.pooled; j[0].has_pool = true;
         j[1].pool = bf.pooled + (size_t)B * H * W * 8; j[1].has_pool = true;
       }
-      if ((rc = r.conv("", bf.R2, 256, 128, 64, 1, false, j, 2))) return rc;
+      if ((rc = r.conv("", bf.R2, 128, 128, 64, 1, false, j, 2))) return rc;
     }
     // CAC gates (:85-118, CAC_module.py:38-63, 78-94)
     float* pooled = reinterpret_cast<float*>(ws + bf.pooled);
@@ -400,17 +410,18 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     const size_t src = k == 0 ? bf.FUSE : bf.OF;
     {
       const int in_off[1] = {0}, out_off[1] = {0};
+      const size_t out_add[1] = {0};
       const char* w3[1] = {"conv9"}; const char* w5[1] = {"conv8"}; const char* wp[1] = {"pair_f"};
       const bool tf[1] = {false};
-      if ((rc = r.pair(src, 64, in_off, w3, w5, wp, tf, bf.MS, 256, out_off, 1))) return rc;
+      if ((rc = r.pair(src, 64, in_off, w3, w5, wp, tf, bf.MS, 128, out_off, out_add, 1))) return rc;
     }
     {
-      LayerJob j[1] = {{"conv10", 0, bf.R2, 256, 0, 0, 0, 0, false}};
-      if ((rc = r.conv("", bf.MS, 256, 128, 128, 5, true, j, 1))) return rc;
+      LayerJob j[1] = {{"conv10", 0, bf.R2, 128, 0, 0, 0, 0, false}};
+      if ((rc = r.conv("", bf.MS, 128, 128, 128, 5, true, j, 1))) return rc;
     }
     {
       LayerJob j[1] = {{"confuse_fuse", 0, bf.OF, 64, 0, bf.FUSE, 64, 0, true}};
-      if ((rc = r.conv("", bf.R2, 256, 128, 64, 1, false, j, 1))) return rc;
+      if ((rc = r.conv("", bf.R2, 128, 128, 64, 1, false, j, 1))) return rc;
     }
   }
   // reconstruction (:129-131): conv11 into the MS region viewed as 64 ch, then output + x
@@ -726,7 +737,7 @@ int codon_debug_tap(codon_ctx* ctx, const char* name, float* dst, int* channels,
   const std::string n(name);
   if (n == "enc") { off = bf.E; C = 128; stride = 128; }
   else if (n == "feat") { off = bf.F; C = 128; stride = 128; }
-  else if (n == "ms") { off = bf.MS; C = 256; stride = 256; }
+  else if (n == "ms") { off = bf.MS; C = 128; stride = 128; }
   else if (n == "fuse") { off = bf.FUSE; C = 64; stride = 64; }
   else if (n == "out_fuse") { off = bf.OF; C = 64; stride = 64; }
   else return fail(ctx, CODON_ERR_ARG, "codon_debug_tap: unknown tap '%s'", name);

@@ -243,7 +243,8 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], const TcJob
 
 template <int NACC, int OPERAND>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcKParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+               const __grid_constant__ TcKParams p) {
   using OutT = typename OperandTraits<OPERAND>::Out;
   using G = Geo<NACC>;
 
@@ -264,7 +265,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   const uint32_t pitch = (uint32_t)p.pw * 128u;    // patch row pitch in bytes
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap1) : "memory");
     for (int i = 0; i < p.npb; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
     for (int i = 0; i < kBStages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 256); }
@@ -295,7 +297,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           if (p.debug & 4) mbar_arrive(bar_patch_full + 8 * ps);
           else {
             mbar_expect_tx(bar_patch_full + 8 * ps, p.patch_tx);
-            tma_load_4d(s_patch + ps * p.patch_stage, &tmap, bar_patch_full + 8 * ps,
+            tma_load_4d(s_patch + ps * p.patch_stage, tl.job ? &tmap1 : &tmap0, bar_patch_full + 8 * ps,
                         job.in_coff + s * p.slab_elems, tl.x0 - p.pad, tl.y0 - p.pad, tl.n);
           }
         }
@@ -546,7 +548,8 @@ __device__ __forceinline__ Tile2 decode_tile2(const TcKParams& p, int item, int 
 
 template <int NACC, int OPERAND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap bmap0,
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+                const __grid_constant__ CUtensorMap bmap0,
                 const __grid_constant__ CUtensorMap bmap1, const __grid_constant__ TcKParams p) {
   using OutT = typename OperandTraits<OPERAND>::Out;
   using G = Geo<NACC>;
@@ -571,7 +574,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const uint32_t pitch = (uint32_t)p.pw * 128u;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap1) : "memory");
     for (int i = 0; i < p.npb; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
@@ -602,7 +606,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
         if (elect_one()) {
           if (leader) mbar_expect_tx(bar_patch_full + 8 * ps, 2 * p.patch_tx);
-          tma_load_4d_2sm(s_patch + ps * p.patch_stage, &tmap, full_leader + 8 * ps,
+          tma_load_4d_2sm(s_patch + ps * p.patch_stage, tl.job ? &tmap1 : &tmap0, full_leader + 8 * ps,
                           coff + s * p.slab_elems, tl.x0 - p.pad, tl.y0 - p.pad, tl.n);
         }
         __syncwarp();
@@ -949,7 +953,7 @@ size_t setup_geometry(TcKParams& kp, int b_stage_bytes_total) {
 }
 
 template <int NACC, int OPERAND>
-cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& b0, const CUtensorMap& b1, TcKParams& kp,
+cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, const CUtensorMap& b0, const CUtensorMap& b1, TcKParams& kp,
                          cudaStream_t st) {
   static bool configured = false;
   static int num_sms = 0;
@@ -972,12 +976,12 @@ cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& b0, const C
     kp.main_tiles = split ? items - rem : items;
     kp.total_items = kp.main_tiles + (items - kp.main_tiles) * NACC;
   }
-  conv_tc2_kernel<NACC, OPERAND><<<2 * clusters, kThreads2, smem, st>>>(tmap, b0, b1, kp);
+  conv_tc2_kernel<NACC, OPERAND><<<2 * clusters, kThreads2, smem, st>>>(tmap, tmapj1, b0, b1, kp);
   return cudaGetLastError();
 }
 
 template <int NACC, int OPERAND>
-cudaError_t launch_nacc(const CUtensorMap& tmap, TcKParams& kp, cudaStream_t st) {
+cudaError_t launch_nacc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, TcKParams& kp, cudaStream_t st) {
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {
@@ -999,12 +1003,13 @@ cudaError_t launch_nacc(const CUtensorMap& tmap, TcKParams& kp, cudaStream_t st)
     kp.total_items = kp.main_tiles + (kp.total_tiles - kp.main_tiles) * NACC;
   }
   const int grid = kp.total_tiles < num_sms ? kp.total_tiles : num_sms;
-  conv_tc_kernel<NACC, OPERAND><<<grid, kThreads, smem, st>>>(tmap, kp);
+  conv_tc_kernel<NACC, OPERAND><<<grid, kThreads, smem, st>>>(tmap, tmapj1, kp);
   return cudaGetLastError();
 }
 }  // namespace
 
-cudaError_t launch_conv_tc(const CUtensorMap& tmap, const TcConvPlan& plan, const TcLaunch& L, cudaStream_t st) {
+cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, const TcConvPlan& plan, const TcLaunch& L,
+                           cudaStream_t st) {
   TcKParams kp;
   memset(&kp, 0, sizeof(kp));
   for (int i = 0; i < L.njobs; ++i) kp.job[i] = L.job[i];
@@ -1035,9 +1040,9 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const TcConvPlan& plan, cons
     const CUtensorMap& b1 = *L.bmap[L.njobs > 1 ? 1 : 0];
 #define CODON_TC2_DISPATCH(N)                                                  \
   switch (plan.operand) {                                                      \
-    case TC_F16: return launch_nacc2<N, TC_F16>(tmap, b0, b1, kp, st);         \
-    case TC_BF16: return launch_nacc2<N, TC_BF16>(tmap, b0, b1, kp, st);       \
-    case TC_TF32: return launch_nacc2<N, TC_TF32>(tmap, b0, b1, kp, st);       \
+    case TC_F16: return launch_nacc2<N, TC_F16>(tmap, tmapj1, b0, b1, kp, st);        \
+    case TC_BF16: return launch_nacc2<N, TC_BF16>(tmap, tmapj1, b0, b1, kp, st);      \
+    case TC_TF32: return launch_nacc2<N, TC_TF32>(tmap, tmapj1, b0, b1, kp, st);      \
     default: return cudaErrorInvalidValue;                                     \
   }
     switch (L.nacc) {
@@ -1050,9 +1055,9 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const TcConvPlan& plan, cons
   }
 #define CODON_TC_DISPATCH(N)                                                   \
   switch (plan.operand) {                                                      \
-    case TC_F16: return launch_nacc<N, TC_F16>(tmap, kp, st);                  \
-    case TC_BF16: return launch_nacc<N, TC_BF16>(tmap, kp, st);                \
-    case TC_TF32: return launch_nacc<N, TC_TF32>(tmap, kp, st);                \
+    case TC_F16: return launch_nacc<N, TC_F16>(tmap, tmapj1, kp, st);                  \
+    case TC_BF16: return launch_nacc<N, TC_BF16>(tmap, tmapj1, kp, st);                \
+    case TC_TF32: return launch_nacc<N, TC_TF32>(tmap, tmapj1, kp, st);                \
     default: return cudaErrorInvalidValue;                                     \
   }
   switch (L.nacc) {

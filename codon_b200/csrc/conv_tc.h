@@ -80,7 +80,8 @@ cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, i
 // 2-D tensor map over a packed weight stream (rows of 128 B, 32-row boxes) for the 2-CTA kernel.
 cudaError_t tc_encode_bmap(CUtensorMap* map, const void* base, size_t bytes);
 
-cudaError_t launch_conv_tc(const CUtensorMap& tmap, const TcConvPlan& plan, const TcLaunch& L,
+// tmap / tmapj1: activation tensor maps of job 0 / job 1 (the same map twice when both jobs read one buffer).
+cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, const TcConvPlan& plan, const TcLaunch& L,
                            cudaStream_t st);
 
 }  // namespace codon

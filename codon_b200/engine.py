@@ -224,7 +224,7 @@ class Engine:
         return out
 
     def debug_tap(self, name: str, B: int, H: int, W: int) -> torch.Tensor:
-        chans = {"enc": 128, "feat": 128, "ms": 256, "fuse": 64, "out_fuse": 64}[name]
+        chans = {"enc": 128, "feat": 128, "ms": 128, "fuse": 64, "out_fuse": 64}[name]
         dst = torch.empty(B, chans, H, W, dtype=torch.float32, device=self.device)
         c = ctypes.c_int(0)
         with torch.cuda.device(self.device):

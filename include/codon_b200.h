@@ -114,7 +114,8 @@ const char* codon_profile_category_name(int category);
 
 /* Copies an intermediate activation of the last forward to dst as fp32 NCHW [B,C,H,W]
  * (DEVICE pointer, C returned through channels).  Names: "enc" (128: depth|colour encoder
- * outputs), "feat" (128: depth|colour stage outputs after the last stage), "ms" (256),
+ * outputs), "feat" (128: depth|colour stage outputs after the last stage), "ms" (128: the
+ * last multi-scale pair of the depth / fusion branch),
  * "fuse" (64), "out_fuse" (64).  For layer-level parity tests. */
 int codon_debug_tap(codon_ctx* ctx, const char* name, float* dst, int* channels,
                     void* cuda_stream);
