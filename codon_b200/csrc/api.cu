@@ -160,7 +160,7 @@ Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W) {
   b.E = take(P * 128 * e); b.F = take(P * 128 * e);
   b.MS = take(P * 256 * e); b.R2 = take(P * 256 * e);
   b.FUSE = take(P * 64 * e); b.OF = take(P * 64 * e);
-  b.pooled = take(P * 2 * 4 * 2);   // (max, mean) map, or two per-branch (max, sum) partial maps
+  b.pooled = take(P * 2 * 4 * 4);   // (max, mean) map, or 2 / 4 (max, sum) partial maps from the 1x1 epilogues
   b.chunks = cac_stats_chunks(B, H, W);
   b.part = take((size_t)B * b.chunks * 256 * 4);
   b.sc = take((size_t)B * 64 * 4);
@@ -287,6 +287,50 @@ struct Runner {
     return CODON_OK;
   }
 
+  // conv5x5 128->128 (+ReLU) immediately followed by conv1x1 128->64 (no ReLU, optional residual) as one
+  // cluster kernel (conv_tc.cu, FUSE).  Returns 1 if the fused path is not applicable (caller falls back).
+  struct FusedJob { const char* w5; const char* w1; size_t in_add; size_t out2; int out2_stride, out2_off;
+                    size_t res2; int res2_stride, res2_off; bool has_res; size_t pool; bool has_pool; };
+  int conv5_fused(size_t in, const FusedJob* jobs, int njobs) {
+    static int env = -2;
+    if (env == -2) { const char* e = getenv("CODON_TC_FUSE"); env = e ? atoi(e) : 1; }
+    if (ctx->mode == CODON_MODE_FP32 || !env) return 1;
+    const int nacc = pick_nacc(B, H, W, njobs, 2, "CODON_TC_NACC_CONV");
+    if (nacc > 2 || !use_two_cta(B, H, W, nacc)) return 1;
+    const TcLayer& l0 = ctx->w_tc.at(jobs[0].w5);
+    TcLaunch L;
+    L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = 1; L.out_act = ctx->act;
+    L.nacc = nacc; L.two_cta = 1; L.fuse = 1;
+    L.y16_operand = ctx->mode == CODON_MODE_BF16 ? TC_BF16 : TC_F16;
+    const CUtensorMap* tm[2] = {nullptr, nullptr};
+    for (int i = 0; i < njobs; ++i) {
+      const TcLayer& l = ctx->w_tc.at(jobs[i].w5);
+      const TcLayer& l1 = ctx->w_tc.at(std::string(jobs[i].w1) + "@y16");
+      L.job[i].in_coff = 0;
+      L.job[i].w = l.dev;
+      L.job[i].out = nullptr; L.job[i].out_stride = 0; L.job[i].out_off = 0;
+      L.job[i].res = nullptr; L.job[i].res_stride = 0; L.job[i].res_off = 0;
+      L.job[i].outer_col = 0;
+      L.job[i].out2 = ws + jobs[i].out2; L.job[i].out2_stride = jobs[i].out2_stride; L.job[i].out2_off = jobs[i].out2_off;
+      L.job[i].res2 = jobs[i].has_res ? ws + jobs[i].res2 : nullptr;
+      L.job[i].res2_stride = jobs[i].res2_stride; L.job[i].res2_off = jobs[i].res2_off;
+      L.job[i].pool = jobs[i].has_pool ? reinterpret_cast<float2*>(ws + jobs[i].pool) : nullptr;
+      L.bmap[i] = &l.bmap;
+      L.wmap[i] = &l1.bmap;
+      int rc = get_tmap(ctx, ws + in + jobs[i].in_add, 128, tc_box_w(l0.plan, nacc), tc_box_h(l0.plan, nacc),
+                        l0.plan.slab_elems, B, H, W, &tm[i]);
+      if (rc) return rc;
+    }
+    const double px = (double)B * H * W;
+    {
+      ProfScope ps(ctx, PC_CONV5_128, 2.0 * px * 128.0 * 128.0 * 25.0 * njobs, st);
+      CU_TRY(ctx, launch_conv_tc(*tm[0], *tm[njobs - 1], l0.plan, L, st));
+    }
+    // the fused 1x1 is booked with zero time: its FLOP stay in the trunk total, its launches are gone
+    ctx->launches++;
+    return CODON_OK;
+  }
+
   static int cat_of(int cin, int cout, int ks) {
     if (ks == 5 && cin == 128) return PC_CONV5_128;
     if (ks == 1) return PC_CONV1;
@@ -365,17 +409,27 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
       const bool tf[2] = {true, false};
       if ((rc = r.pair(src, 128, in_off, w3, w5, wp, tf, bf.MS, 128, out_off, out_add, 2))) return rc;
     }
+    const size_t pmap = (size_t)B * H * W * 8;     // bytes of one per-pixel float2 partial map
+    int pool_parts = 1;
     {
-      LayerJob j[2] = {{"conv3", 0, bf.R2, 128, 0, 0, 0, 0, false}, {"conv6", 0, bf.R2 + half, 128, 0, 0, 0, 0, false}};
-      j[1].in_add = half;
-      if ((rc = r.conv("", bf.MS, 128, 128, 128, 5, true, j, 2))) return rc;
+      Runner::FusedJob fj[2] = {{"conv3", "confuse", 0, bf.F, 128, 0, 0, 0, 0, false, bf.pooled, true},
+                                {"conv6", "confuse_c", half, bf.F, 128, 64, 0, 0, 0, false, bf.pooled + 2 * pmap, true}};
+      rc = r.conv5_fused(bf.MS, fj, 2);
+      if (rc < 0) return rc;
+      if (rc == 0) pool_parts = 4;
     }
-    {
+    if (pool_parts == 1) {
+      {
+        LayerJob j[2] = {{"conv3", 0, bf.R2, 128, 0, 0, 0, 0, false}, {"conv6", 0, bf.R2 + half, 128, 0, 0, 0, 0, false}};
+        j[1].in_add = half;
+        if ((rc = r.conv("", bf.MS, 128, 128, 128, 5, true, j, 2))) return rc;
+      }
       LayerJob j[2] = {{"confuse", 0, bf.F, 128, 0, 0, 0, 0, false}, {"confuse_c", 0, bf.F, 128, 64, 0, 0, 0, false}};
       j[1].in_add = half;
       if (tc_mode) {   // the 1x1 epilogues emit the per-branch ChannelPool partials (max, sum) per pixel
         j[0].pool = bf.pooled; j[0].has_pool = true;
-        j[1].pool = bf.pooled + (size_t)B * H * W * 8; j[1].has_pool = true;
+        j[1].pool = bf.pooled + pmap; j[1].has_pool = true;
+        pool_parts = 2;
       }
       if ((rc = r.conv("", bf.R2, 128, 128, 64, 1, false, j, 2))) return rc;
     }
@@ -396,7 +450,7 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     }
     {
       ProfScope ps(ctx, PC_CAC_APPLY, P * 384 * r.e, st);
-      CU_TRY(ctx, launch_cac_apply(ws + bf.F, ws + bf.E, ctx->act, pooled, sc, ctx->cac_ws[s], B, H, W, st, ctx->mode == CODON_MODE_TF32, tc_mode ? 2 : 1));
+      CU_TRY(ctx, launch_cac_apply(ws + bf.F, ws + bf.E, ctx->act, pooled, sc, ctx->cac_ws[s], B, H, W, st, ctx->mode == CODON_MODE_TF32, pool_parts));
     }
     ctx->launches += 3;
   }
@@ -416,10 +470,15 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
       if ((rc = r.pair(src, 64, in_off, w3, w5, wp, tf, bf.MS, 128, out_off, out_add, 1))) return rc;
     }
     {
-      LayerJob j[1] = {{"conv10", 0, bf.R2, 128, 0, 0, 0, 0, false}};
-      if ((rc = r.conv("", bf.MS, 128, 128, 128, 5, true, j, 1))) return rc;
+      Runner::FusedJob fj[1] = {{"conv10", "confuse_fuse", 0, bf.OF, 64, 0, bf.FUSE, 64, 0, true, 0, false}};
+      rc = r.conv5_fused(bf.MS, fj, 1);
+      if (rc < 0) return rc;
     }
-    {
+    if (rc == 1) {
+      {
+        LayerJob j[1] = {{"conv10", 0, bf.R2, 128, 0, 0, 0, 0, false}};
+        if ((rc = r.conv("", bf.MS, 128, 128, 128, 5, true, j, 1))) return rc;
+      }
       LayerJob j[1] = {{"confuse_fuse", 0, bf.OF, 64, 0, bf.FUSE, 64, 0, true}};
       if ((rc = r.conv("", bf.R2, 128, 128, 64, 1, false, j, 1))) return rc;
     }
@@ -578,6 +637,16 @@ int codon_finalize_weights(codon_ctx* ctx) {
       if ((rc = upload(ctx, packed, &l.dev))) return rc;
       CU_TRY(ctx, tc_encode_bmap(&l.bmap, l.dev, packed.size()));
       ctx->w_tc[s.name] = l;
+    }
+    // 16-bit copies of the 1x1 weights for the fused conv5+1x1 kernel (fp16 in tf32 mode: same mantissa width)
+    const int y16 = operand == TC_BF16 ? TC_BF16 : TC_F16;
+    for (const char* n : {"confuse", "confuse_c", "confuse_fuse"}) {
+      TcLayer l;
+      l.plan = tc_make_plan(1, 128, 64, y16);
+      tc_pack_weights(l.plan, W(n).data.data(), packed);
+      if ((rc = upload(ctx, packed, &l.dev))) return rc;
+      CU_TRY(ctx, tc_encode_bmap(&l.bmap, l.dev, packed.size()));
+      ctx->w_tc[std::string(n) + "@y16"] = l;
     }
     struct PairSpec { const char* name; const char* w3; const char* w5; bool three_first; };
     // depth [3x3|5x5] (:75,77,79); colour [5x5|3x3] (:76,78,80); fusion [5x5|3x3] (:123-125)

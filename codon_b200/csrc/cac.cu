@@ -258,10 +258,14 @@ __global__ void __launch_bounds__(256) cac_apply_kernel(T* __restrict__ F, const
     float2 v = make_float2(0.f, 0.f);
     if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
       v = __ldg(reinterpret_cast<const float2*>(pooled + (fb + (size_t)gy * W + gx) * 2));
-      if (pool_parts == 2) {
-        // two per-branch (max, sum) partials from the 1x1 conv epilogues -> (max, mean) over the 128 channels
-        const float2 w = __ldg(reinterpret_cast<const float2*>(pooled + (part_stride + fb + (size_t)gy * W + gx) * 2));
-        v = make_float2(fmaxf(v.x, w.x), (v.y + w.y) * (1.0f / 128.0f));
+      if (pool_parts > 1) {
+        // (max, sum) partials from the 1x1 conv epilogues (2: one per branch; 4: per branch and 32-channel half)
+        // -> (max, mean) over the 128 channels
+        for (int k = 1; k < pool_parts; ++k) {
+          const float2 w = __ldg(reinterpret_cast<const float2*>(pooled + ((size_t)k * part_stride + fb + (size_t)gy * W + gx) * 2));
+          v = make_float2(fmaxf(v.x, w.x), v.y + w.y);
+        }
+        v.y *= (1.0f / 128.0f);
       }
     }
     sp[i / PW][i % PW] = v;

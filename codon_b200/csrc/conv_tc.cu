@@ -61,6 +61,8 @@ struct TcKParams {
   int pw;                        // patch width in pixels (tile_w + ks - 1); the patch row pitch is pw * 128 B
   uint32_t patch_tx, patch_stage;   // bytes of one patch (TMA transaction) and of one patch stage (1024-aligned)
   int npb;                       // patch stages in the ring (2 .. kMaxNPB)
+  uint32_t idesc_1x1;            // fused 1x1: kind::f16, M = 256, N = 64
+  int fuse_njobs;
   int debug;   // CODON_TC_DEBUG bits (perf experiments only, 1-CTA kernel): 1 no epilogue stores, 2 no B loads, 4 no A loads, 8 no MMAs, 16 no waits
 };
 
@@ -517,6 +519,33 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, u
 }
 
 
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// non-blocking phase test with cluster-scope acquire (the arrivals come from both CTAs of the pair)
+__device__ __forceinline__ bool mbar_test_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+template <int OP16> __device__ __forceinline__ uint32_t pack16(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack16<TC_BF16>(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack16<TC_F16>(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 struct Tile2 { int job, n, y0, x0, valid, nacc; };
 // Work item -> this CTA's tile.  Items [0, main_tiles) are pair-tiles (tiles 2q and 2q+1 of a job);
 // the pair-tiles of the last partial wave are handed out as NACC single-sub-tile items each.
@@ -546,13 +575,21 @@ __device__ __forceinline__ Tile2 decode_tile2(const TcKParams& p, int item, int 
   return r;
 }
 
-template <int NACC, int OPERAND>
+// FUSE: the launch is a 5x5 128->128 (+ReLU) convolution followed by a 1x1 128->64 convolution (confuse /
+// confuse_c / confuse_fuse, CODON_x4.py:83-84,127).  The epilogue drains each accumulator through ReLU into a
+// 16-bit K-major SWIZZLE_128B tile Y in shared memory (fence.proxy.async), the MMA issuer multiplies it with
+// the resident 1x1 weights (8 MMAs, N = 64) into the first 64 columns of the same accumulator, and the
+// epilogue drains those (+ the fusion-stage residual) to global memory.  The 128-channel intermediate never
+// touches HBM and the stand-alone 1x1 launch disappears.
+template <int NACC, int OPERAND, bool FUSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
-                const __grid_constant__ CUtensorMap bmap0,
-                const __grid_constant__ CUtensorMap bmap1, const __grid_constant__ TcKParams p) {
+                const __grid_constant__ CUtensorMap bmap0, const __grid_constant__ CUtensorMap bmap1,
+                const __grid_constant__ CUtensorMap wmap0, const __grid_constant__ CUtensorMap wmap1,
+                const __grid_constant__ TcKParams p) {
   using OutT = typename OperandTraits<OPERAND>::Out;
   using G = Geo<NACC>;
+  constexpr int Y16 = OPERAND == TC_BF16 ? TC_BF16 : TC_F16;   // tf32 mode stages Y in fp16 (same 10-bit mantissa)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -562,9 +599,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * kMaxNPB;
   const uint32_t bar_b_full = s_bar + 16 * kMaxNPB, bar_b_empty = bar_b_full + 8 * kB2Stages;
   const uint32_t bar_acc_full = bar_b_empty + 8 * kB2Stages, bar_acc_empty = bar_acc_full + 16;
-  const uint32_t s_tmem_slot = bar_acc_empty + 16;
+  const uint32_t bar_y_full = bar_acc_empty + 16, bar_y_done = bar_y_full + 8, bar_wc_full = bar_y_done + 8;
+  const uint32_t s_tmem_slot = bar_wc_full + 8;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (s_tmem_slot - smem_u32(smem_raw)));
+  // fused mode: [1x1 weights: 2 jobs x 2 slabs x 32 rows x 128 B = 16 KB][Y: 2 slabs x 128 rows x 128 B = 32 KB]
+  const uint32_t s_wc = s_b + kB2Stages * kB2StageBytes;
+  const uint32_t s_y = s_wc + 16384;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -581,6 +622,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     for (int i = 0; i < p.npb; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
     for (int i = 0; i < kB2Stages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 512); }
+    mbar_init(bar_y_full, 512); mbar_init(bar_y_done, 1); mbar_init(bar_wc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -618,6 +660,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     int bs = 0;
     uint32_t bph = 0;
     const uint32_t full_leader = mapa_u32(bar_b_full, 0);
+    if (FUSE && elect_one()) {
+      // resident 1x1 weights: this CTA's 32 of the 64 output rows, per job and 128-byte K slab
+      if (leader) mbar_expect_tx(bar_wc_full, (uint32_t)p.fuse_njobs * 2u * 8192u);
+      const uint32_t wc_leader = mapa_u32(bar_wc_full, 0);
+      for (int jb = 0; jb < p.fuse_njobs; ++jb)
+        for (int sl = 0; sl < 2; ++sl)
+          tma_load_2d_2sm(s_wc + (uint32_t)(jb * 2 + sl) * 4096u, jb ? &wmap1 : &wmap0, wc_leader, 0,
+                          (int)((sl * 8192u + rank * 4096u) >> 7));
+    }
+    __syncwarp();
     for (int item = cluster_id; item < total_items; item += nclusters) {
       const Tile2 tl = decode_tile2<NACC>(p, item, (int)rank);
       const CUtensorMap* bm = tl.job ? &bmap1 : &bmap0;
@@ -646,12 +698,42 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
       uint32_t pph = 0, bph = 0;
       int it = 0;
       const uint64_t desc_a = umma_desc_hi(pitch), desc_b = umma_desc_hi(1024);
+      // fused 1x1: uses (accumulators) of the previous tile that are still to be multiplied
+      int prev_left = 0, prev_j = 0, prev_job = 0;
+      uint32_t prev_d = 0, y_uses = 0;
+      bool wc_ready = false;
+      auto service = [&](bool block) {
+        // issues the 1x1 MMAs of the next pending accumulator once its Y tile is complete in both CTAs
+        while (prev_left > 0) {
+          if (block) { while (!mbar_test_cluster(bar_y_full, y_uses & 1u)) {} }
+          else if (!mbar_test_cluster(bar_y_full, y_uses & 1u)) return;
+          if (!wc_ready) { mbar_wait(bar_wc_full, 0); wc_ready = true; }
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d = prev_d + (uint32_t)(prev_j * 128);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t ad = desc_b | desc_addr(s_y + (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u);
+              const uint64_t bd = desc_b | desc_addr(s_wc + (uint32_t)(prev_job * 2 + (k >> 2)) * 4096u + (uint32_t)(k & 3) * 32u);
+              umma_f16_2sm(d, ad, bd, p.idesc_1x1, k ? 1u : 0u);
+            }
+            umma_commit_2sm(bar_y_done);
+          }
+          __syncwarp();
+          ++y_uses; ++prev_j; --prev_left;
+        }
+      };
       for (int item = cluster_id; item < total_items; item += nclusters, ++it) {
         const Tile2 tl = decode_tile2<NACC>(p, item, 0);
         const int outer_col = p.job[tl.job].outer_col;
         const int buf = it % p.nbuf;
         const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
-        mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
+        if (FUSE) {
+          // the epilogue of the tile that last used this TMEM buffer needs our 1x1 MMAs to finish: keep serving
+          while (!mbar_test_cluster(bar_acc_empty + 8 * buf, aph ^ 1)) service(false);
+        } else {
+          mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
+        }
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(buf * NACC * p.n_cols);
         uint32_t acc0 = 0;
@@ -660,6 +742,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           const uint32_t patch = s_patch + ps * p.patch_stage;
           for (int dxi = 0; dxi < p.ndx; ++dxi) {
             for (int dyi = 0; dyi < p.ndy; ++dyi) {
+              if (FUSE) service(false);
               mbar_wait(bar_b_full + 8 * bs, bph);
               tc_fence_after();
               const bool half = p.b_bytes[dxi][dyi] < (uint32_t)p.n_cols * 128u;
@@ -691,7 +774,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           }
           if (++ps == p.npb) { ps = 0; pph ^= 1; }
         }
+        if (FUSE) {
+          service(true);                       // anything still pending belongs to the tile before this one
+          prev_left = tl.nacc; prev_j = 0; prev_job = tl.job; prev_d = d_base;
+        }
       }
+      if (FUSE) service(true);
     }
   } else {
     // ================================ epilogue (both CTAs, own tile) ==============================
@@ -700,6 +788,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     const int m = q * 32 + lane;
     const int my = m / kTcSubW, mx = m % kTcSubW;
     const uint32_t acc_empty_leader = mapa_u32(bar_acc_empty, 0);
+    const uint32_t y_full_leader = mapa_u32(bar_y_full, 0);
+    uint32_t y_uses = 0;                         // fused mode: Y hand-offs so far (phase of y_full / y_done)
     int it = 0;
     for (int item = cluster_id; item < total_items; item += nclusters, ++it) {
       const Tile2 tl = decode_tile2<NACC>(p, item, (int)rank);
@@ -707,32 +797,90 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
       const int buf = it % p.nbuf;
       mbar_wait(bar_acc_full + 8 * buf, (uint32_t)(it / p.nbuf) & 1u);
       tc_fence_after();
-      const int cpa_sh = p.n_cols == 128 ? 2 : 1, nchunk = tl.nacc << cpa_sh;    // chunks per accumulator: 4 or 2
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NACC * p.n_cols);
-      auto issue = [&](int i, uint32_t (&r)[32]) { tmem_ld32(lane_base + (uint32_t)(i << 5), r); };
-      auto drain = [&](int i, const uint32_t (&r)[32]) {
-        const int j = i >> cpa_sh, c0 = (i - (j << cpa_sh)) << 5;
-        const int py = tl.y0 + (j / G::NAX) * kTcSubH + my, px = tl.x0 + (j % G::NAX) * kTcSubW + mx;
-        if (tl.valid && (py < p.H) && (px < p.W)) {
-          const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
-          store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32);
+      if (FUSE) {
+        // accumulator j -> ReLU -> 16-bit -> Y (this warp: the 64 channels of slab `ehalf`), then the 1x1 result
+        // (64 columns at the start of the same accumulator; this warp: 32 of them) -> (+ res2) -> out2
+        auto stage_y = [&](int j) {
+          uint32_t ra[32], rb[32];
+          tmem_ld32(lane_base + (uint32_t)(j * 128 + ehalf * 64), ra);
+          tmem_ld32(lane_base + (uint32_t)(j * 128 + ehalf * 64 + 32), rb);
+          tmem_ld_wait();
+          const uint32_t row = s_y + (uint32_t)ehalf * 16384u + (uint32_t)m * 128u;
+#pragma unroll
+          for (int pc = 0; pc < 8; ++pc) {
+            const uint32_t* r = pc < 4 ? ra : rb;
+            const int e0 = (pc & 3) * 8;
+            uint32_t w[4];
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2)
+              w[t2] = pack16<Y16>(fmaxf(__uint_as_float(r[e0 + 2 * t2]), 0.f), fmaxf(__uint_as_float(r[e0 + 2 * t2 + 1]), 0.f));
+            st_shared_v4(row + (uint32_t)((pc ^ (m & 7)) << 4), w[0], w[1], w[2], w[3]);
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive_cluster_release(y_full_leader);
+        };
+        auto drain_d2 = [&](int j) {
+          uint32_t r[32];
+          tmem_ld32(lane_base + (uint32_t)(j * 128 + ehalf * 32), r);
+          tmem_ld_wait();
+          const int py = tl.y0 + (j / G::NAX) * kTcSubH + my, px = tl.x0 + (j % G::NAX) * kTcSubW + mx;
+          if (tl.valid && (py < p.H) && (px < p.W)) {
+            const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
+            TcJob o2 = job;
+            o2.out = job.out2; o2.out_stride = job.out2_stride; o2.out_off = job.out2_off;
+            o2.res = job.res2; o2.res_stride = job.res2_stride; o2.res_off = job.res2_off;
+            store_chunk<OutT>(r, o2, pix, ehalf * 32, false, OPERAND == TC_TF32);
+            if (job.pool) {
+              // ChannelPool partial (max, sum) over this thread's 32 of the job's 64 channels: pool[half][pixel]
+              float mxv = __uint_as_float(r[0]), sacc = 0.f;
+#pragma unroll
+              for (int e = 0; e < 32; ++e) { const float v = __uint_as_float(r[e]); mxv = fmaxf(mxv, v); sacc += v; }
+              job.pool[(size_t)ehalf * ((size_t)p.B * p.H * p.W) + pix] = make_float2(mxv, sacc);
+            }
+          }
+        };
+        // Y is free here: the previous hand-off's y_done was awaited before its drain
+        stage_y(0);
+        for (int j = 1; j < tl.nacc; ++j) {
+          mbar_wait(bar_y_done, y_uses & 1u);    // 1x1 of accumulator j-1 finished: Y is free, its result is in TMEM
+          ++y_uses;
+          tc_fence_after();
+          stage_y(j);
+          drain_d2(j - 1);
         }
-      };
-      // the two warps of a lane quarter take the even / odd chunks
-      uint32_t ra[32], rb[32];
-      int i = ehalf;
-      issue(i, ra);
+        mbar_wait(bar_y_done, y_uses & 1u);
+        ++y_uses;
+        tc_fence_after();
+        drain_d2(tl.nacc - 1);
+      } else {
+        const int cpa_sh = p.n_cols == 128 ? 2 : 1, nchunk = tl.nacc << cpa_sh;    // chunks per accumulator: 4 or 2
+        auto issue = [&](int i, uint32_t (&r)[32]) { tmem_ld32(lane_base + (uint32_t)(i << 5), r); };
+        auto drain = [&](int i, const uint32_t (&r)[32]) {
+          const int j = i >> cpa_sh, c0 = (i - (j << cpa_sh)) << 5;
+          const int py = tl.y0 + (j / G::NAX) * kTcSubH + my, px = tl.x0 + (j % G::NAX) * kTcSubW + mx;
+          if (tl.valid && (py < p.H) && (px < p.W)) {
+            const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
+            store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32);
+          }
+        };
+        // the two warps of a lane quarter take the even / odd chunks
+        uint32_t ra[32], rb[32];
+        int i = ehalf;
+        issue(i, ra);
 #pragma unroll 1
-      while (true) {
-        tmem_ld_wait();
-        if (i + 2 < nchunk) issue(i + 2, rb);
-        drain(i, ra);
-        if (i + 2 >= nchunk) break;
-        tmem_ld_wait();
-        if (i + 4 < nchunk) issue(i + 4, ra);
-        drain(i + 2, rb);
-        if (i + 4 >= nchunk) break;
-        i += 4;
+        while (true) {
+          tmem_ld_wait();
+          if (i + 2 < nchunk) issue(i + 2, rb);
+          drain(i, ra);
+          if (i + 2 >= nchunk) break;
+          tmem_ld_wait();
+          if (i + 4 < nchunk) issue(i + 4, ra);
+          drain(i + 2, rb);
+          if (i + 4 >= nchunk) break;
+          i += 4;
+        }
       }
       tc_fence_before();
       mbar_arrive_cluster(acc_empty_leader + 8 * buf);
@@ -952,20 +1100,21 @@ size_t setup_geometry(TcKParams& kp, int b_stage_bytes_total) {
   return fixed + (size_t)npb * kp.patch_stage;
 }
 
-template <int NACC, int OPERAND>
-cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, const CUtensorMap& b0, const CUtensorMap& b1, TcKParams& kp,
-                         cudaStream_t st) {
+template <int NACC, int OPERAND, bool FUSE>
+cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, const CUtensorMap& b0, const CUtensorMap& b1,
+                         const CUtensorMap& w0, const CUtensorMap& w1, TcKParams& kp, cudaStream_t st) {
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NACC, OPERAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NACC, OPERAND, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  const size_t smem = setup_geometry<NACC>(kp, kB2Stages * kB2StageBytes);
+  // fused mode adds the resident 1x1 weights (16 KB) and the Y staging tile (32 KB) behind the B ring
+  const size_t smem = setup_geometry<NACC>(kp, kB2Stages * kB2StageBytes + (FUSE ? 49152 : 0));
   if (!smem) return cudaErrorInvalidConfiguration;
   const int items = ((kp.tiles_per_job + 1) / 2) * kp.njobs;     // pair-tiles
   int clusters = num_sms / 2;
@@ -976,7 +1125,7 @@ cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, con
     kp.main_tiles = split ? items - rem : items;
     kp.total_items = kp.main_tiles + (items - kp.main_tiles) * NACC;
   }
-  conv_tc2_kernel<NACC, OPERAND><<<2 * clusters, kThreads2, smem, st>>>(tmap, tmapj1, b0, b1, kp);
+  conv_tc2_kernel<NACC, OPERAND, FUSE><<<2 * clusters, kThreads2, smem, st>>>(tmap, tmapj1, b0, b1, w0, w1, kp);
   return cudaGetLastError();
 }
 
@@ -1033,17 +1182,39 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, c
   if (L.out_act != (plan.operand == TC_TF32 ? ACT_F32 : plan.operand == TC_BF16 ? ACT_BF16 : ACT_F16))
     return cudaErrorInvalidValue;   // activations are stored in the operand type
   for (int i = 0; i < L.njobs; ++i)
-    if (L.job[i].pool && (plan.n_cols != 64 || L.two_cta)) return cudaErrorInvalidValue;
+    if (L.job[i].pool && !L.fuse && (plan.n_cols != 64 || L.two_cta)) return cudaErrorInvalidValue;
   if (L.two_cta) {
     if (!L.bmap[0] || (L.njobs > 1 && !L.bmap[1])) return cudaErrorInvalidValue;
     const CUtensorMap& b0 = *L.bmap[0];
     const CUtensorMap& b1 = *L.bmap[L.njobs > 1 ? 1 : 0];
-#define CODON_TC2_DISPATCH(N)                                                  \
-  switch (plan.operand) {                                                      \
-    case TC_F16: return launch_nacc2<N, TC_F16>(tmap, tmapj1, b0, b1, kp, st);        \
-    case TC_BF16: return launch_nacc2<N, TC_BF16>(tmap, tmapj1, b0, b1, kp, st);      \
-    case TC_TF32: return launch_nacc2<N, TC_TF32>(tmap, tmapj1, b0, b1, kp, st);      \
-    default: return cudaErrorInvalidValue;                                     \
+    if (L.fuse) {
+      if (plan.ks != 5 || plan.n_cols != 128 || plan.pair || L.nacc > 2 || !L.wmap[0] || (L.njobs > 1 && !L.wmap[1]) ||
+          L.y16_operand != (plan.operand == TC_BF16 ? TC_BF16 : TC_F16))
+        return cudaErrorInvalidValue;
+      kp.idesc_1x1 = make_idesc(L.y16_operand, 64, 256);
+      kp.fuse_njobs = L.njobs;
+      const CUtensorMap& w0 = *L.wmap[0];
+      const CUtensorMap& w1 = *L.wmap[L.njobs > 1 ? 1 : 0];
+#define CODON_TC2F_DISPATCH(N)                                                          \
+  switch (plan.operand) {                                                               \
+    case TC_F16: return launch_nacc2<N, TC_F16, true>(tmap, tmapj1, b0, b1, w0, w1, kp, st);   \
+    case TC_BF16: return launch_nacc2<N, TC_BF16, true>(tmap, tmapj1, b0, b1, w0, w1, kp, st); \
+    case TC_TF32: return launch_nacc2<N, TC_TF32, true>(tmap, tmapj1, b0, b1, w0, w1, kp, st); \
+    default: return cudaErrorInvalidValue;                                              \
+  }
+      switch (L.nacc) {
+        case 1: CODON_TC2F_DISPATCH(1)
+        case 2: CODON_TC2F_DISPATCH(2)
+        default: return cudaErrorInvalidValue;
+      }
+#undef CODON_TC2F_DISPATCH
+    }
+#define CODON_TC2_DISPATCH(N)                                                           \
+  switch (plan.operand) {                                                               \
+    case TC_F16: return launch_nacc2<N, TC_F16, false>(tmap, tmapj1, b0, b1, b0, b1, kp, st);  \
+    case TC_BF16: return launch_nacc2<N, TC_BF16, false>(tmap, tmapj1, b0, b1, b0, b1, kp, st);\
+    case TC_TF32: return launch_nacc2<N, TC_TF32, false>(tmap, tmapj1, b0, b1, b0, b1, kp, st);\
+    default: return cudaErrorInvalidValue;                                              \
   }
     switch (L.nacc) {
       case 1: CODON_TC2_DISPATCH(1)

@@ -51,6 +51,9 @@ struct TcJob {
   void* out;       int out_stride; int out_off;   // elements
   const void* res; int res_stride; int res_off;
   int outer_col;               // pair plans: accumulator column of the 5x5-only (outer) taps
+  // fused 1x1 (TcLaunch::fuse): out2 = conv1x1(relu(this conv)) (+ res2), 64 channels of the activation type
+  void* out2 = nullptr;       int out2_stride = 0; int out2_off = 0;
+  const void* res2 = nullptr; int res2_stride = 0; int res2_off = 0;
   float2* pool;                // optional (64-column launches, 1-CTA kernel): per-pixel (max, sum) over this job's
                                // 64 output channels -> pool[pixel]; the CAC ChannelPool partial (CAC_module.py:78-81)
 };
@@ -62,6 +65,10 @@ struct TcLaunch {
   int relu = 0;
   int out_act = 0;             // ActType of out / res
   int nacc = 4;                // accumulators (128-pixel sub-tiles) per CTA tile: 1, 2 or 4
+  int fuse = 0;                // 1 (two_cta, 5x5 128->128 only): the following 1x1 128->64 convolution runs as a second
+                               // GEMM out of TMEM inside the same kernel (job.out2 / res2, wmap); job.out is not written
+  int y16_operand = TC_BF16;   // 16-bit type of the staged ReLU output and of the 1x1 weights (TC_F16 / TC_BF16)
+  const CUtensorMap* wmap[2] = {nullptr, nullptr};   // per job: 2-D map of the packed 1x1 weight stream
   int two_cta = 0;             // 1: cluster-of-2 kernel (tcgen05 cta_group::2, M = 256); needs bmap
   const CUtensorMap* bmap[2] = {nullptr, nullptr};   // per job: 2-D map of the packed weight stream
 };
