@@ -274,7 +274,13 @@ struct Runner {
       L.bmap[i] = &l.bmap;
     }
     // the HBM-bound 1x1 / 3x3 layers measured slower in cluster mode; the 5x5 layers gain 15-20 %
-    L.two_cta = ks == 5 ? use_two_cta(B, H, W, L.nacc) : 0;
+    {
+      static int all = -1;
+      if (all < 0) { const char* e = getenv("CODON_TC_2CTA_ALL"); all = e ? atoi(e) : 0; }
+      // cluster mode: the 5x5 layers (+15-20 %) and, with one patch per slab, the 3x3 layers (+30 %); the
+      // stand-alone 1x1 (fallback path only) stays single-CTA: its epilogue emits the ChannelPool partials
+      L.two_cta = (ks == 5 || ks == 3 || (all && !jobs[0].has_pool)) ? use_two_cta(B, H, W, L.nacc) : 0;
+    }
     const CUtensorMap* tm[2] = {nullptr, nullptr};
     for (int i = 0; i < njobs; ++i) {
       int rc = get_tmap(ctx, ws + in + jobs[i].in_add, in_C, tc_box_w(l0.plan, L.nacc), tc_box_h(l0.plan, L.nacc),

@@ -9,27 +9,33 @@ namespace codon {
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// first conv: each thread produces one 16-byte vector (kVec channels) of one pixel of one branch.
-// out is NHWC with 128 channels: [depth 0..63 | colour 64..127].
+// first conv: a thread owns one 16-byte channel vector (kVec channels of one branch) for ALL the pixels
+// it visits, so its 9 x kVec weights live in registers (the r01 version re-read them from shared memory
+// with 4-way bank conflicts and ran at ~0.8 TB/s).  out is NHWC with 128 channels: [depth | colour].
 template <typename T>
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x,
                                                          const float* __restrict__ y,
                                                          const float* __restrict__ w_d,
                                                          const float* __restrict__ w_c,
                                                          T* __restrict__ out, int B, int H, int W, int rnd_tf32) {
-  constexpr int V = Act<T>::kVec, LPP = 128 / V;   // lanes per pixel
-  __shared__ float sw[2][9][64];
-  for (int i = threadIdx.x; i < 2 * 9 * 64; i += blockDim.x)
-    sw[i / 576][(i % 576) / 64][i % 64] = (i < 576 ? w_d[i] : w_c[i - 576]);
-  __syncthreads();
-  const size_t total = (size_t)B * H * W * LPP;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % LPP);
-    const size_t pix = idx / LPP;
-    const int c0 = g * V, br = c0 >> 6, c = c0 & 63;
-    const int gx = (int)(pix % W), gy = (int)((pix / W) % H);
-    const float* src = (br ? y : x) + (pix - (size_t)gy * W - gx);   // frame base
+  constexpr int V = Act<T>::kVec, LPP = 128 / V, PPB = 256 / LPP;   // lanes per pixel, pixels per CTA pass
+  const int g = threadIdx.x % LPP, sub = threadIdx.x / LPP;
+  const int c0 = g * V, br = c0 >> 6, c = c0 & 63;
+  float w[9][V];
+  {
+    const float* wsrc = br ? w_c : w_d;
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < V; ++j) w[t][j] = __ldg(wsrc + t * 64 + c + j);
+  }
+  const float* img = br ? y : x;
+  // 32-bit pixel arithmetic: codon_forward bounds B*H*W below 2^30 (64-bit div/mod dominated the r01 loop)
+  const uint32_t npix = (uint32_t)B * H * W;
+  for (uint32_t pix = blockIdx.x * PPB + sub; pix < npix; pix += gridDim.x * PPB) {
+    const uint32_t row = pix / (uint32_t)W;
+    const int gx = (int)(pix - row * W), gy = (int)(row % (uint32_t)H);
+    const float* src = img + (size_t)(pix - (uint32_t)gy * W - gx);   // frame base
     float in[9];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
@@ -43,35 +49,38 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
     for (int j = 0; j < V; ++j) {
       float a = 0.f;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) a = fmaf(in[t], sw[br][t][c + j], a);
+      for (int t = 0; t < 9; ++t) a = fmaf(in[t], w[t][j], a);
       v[j] = fmaxf(a, 0.f);
       if (rnd_tf32) v[j] = round_tf32(v[j]);
     }
-    Act<T>::store(out + pix * 128 + c0, v);
+    Act<T>::store(out + (size_t)pix * 128 + c0, v);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // last conv: LPP lanes cooperate on one pixel (each lane owns one 16-byte channel vector for all
-// 9 taps), then a shuffle reduction; lane 0 of the group adds the global residual and writes.
+// 9 taps, weights in registers), then a shuffle reduction; lane 0 of the group adds the global
+// residual and writes.
 template <typename T>
 __global__ void __launch_bounds__(256) conv_last_kernel(const T* __restrict__ in, int in_stride,
                                                         const float* __restrict__ w,
                                                         const float* __restrict__ x,
                                                         float* __restrict__ out, int B, int H, int W) {
-  constexpr int V = Act<T>::kVec, LPP = 64 / V;
-  __shared__ float sw[9][64];
-  for (int i = threadIdx.x; i < 576; i += blockDim.x) sw[i / 64][i % 64] = w[i];
-  __syncthreads();
-  const size_t npix = (size_t)B * H * W;
-  const size_t total = (npix * LPP + 31) / 32 * 32;   // keep whole warps in the shuffle
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % LPP);
-    const size_t pix = idx / LPP;
+  constexpr int V = Act<T>::kVec, LPP = 64 / V, PPB = 256 / LPP;
+  const int g = threadIdx.x % LPP, sub = threadIdx.x / LPP;
+  float wr[9][V];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < V; ++j) wr[t][j] = __ldg(w + t * 64 + g * V + j);
+  const uint32_t npix = (uint32_t)B * H * W;
+  const uint32_t npass = (npix + PPB - 1) / PPB;            // whole warps stay in the loop (shuffles)
+  for (uint32_t pass = blockIdx.x; pass < npass; pass += gridDim.x) {
+    const uint32_t pix = pass * PPB + sub;
     float a = 0.f;
     if (pix < npix) {
-      const int gx = (int)(pix % W), gy = (int)((pix / W) % H);
+      const uint32_t row = pix / (uint32_t)W;
+      const int gx = (int)(pix - row * W), gy = (int)(row % (uint32_t)H);
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
@@ -79,9 +88,9 @@ __global__ void __launch_bounds__(256) conv_last_kernel(const T* __restrict__ in
           const int yy = gy + dy - 1, xx = gx + dx - 1;
           if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
             float v[V];
-            Act<T>::load(in + (pix + (size_t)(dy - 1) * W + (dx - 1)) * in_stride + g * V, v);
+            Act<T>::load(in + ((size_t)pix + (size_t)((dy - 1) * W + (dx - 1))) * in_stride + g * V, v);
 #pragma unroll
-            for (int j = 0; j < V; ++j) a = fmaf(v[j], sw[dy * 3 + dx][g * V + j], a);
+            for (int j = 0; j < V; ++j) a = fmaf(v[j], wr[dy * 3 + dx][j], a);
           }
         }
     }
