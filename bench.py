@@ -16,8 +16,9 @@ One JSON line is printed by rank 0 (see the driver contract in the task descript
   value        device-timed throughput, frames resident in HBM (CUDA events, max over ranks)
   e2e          the same metric through the host entry point (codon_forward_host: pinned H2D of
                the two frames + forward + D2H of the result inside the timed region)
-  roofline     dominant kernel (5x5 128->128 tcgen05 implicit GEMM): algorithmic FLOP / CUDA-event
-               time of its launches inside the timed region, against MEASURED_PEAKS.json
+  roofline     dominant kernel (5x5 128->128 tcgen05 implicit GEMM with the fused 1x1): algorithmic FLOP
+               of the 5x5 alone / CUDA-event time of its launches inside the timed region, against
+               MEASURED_PEAKS.json
   cpu_baseline the oracle's CPU forward (torch fp32, all host cores) on a bounded sample
 --impl reference times that CPU forward alone, as the reference arm.
 """
@@ -281,9 +282,15 @@ def run_gpu(a):
     cac_bytes = prof["cac_stats"]["work"] + prof["cac_apply"]["work"]
     all_ms = sum(v["ms"] for v in prof.values())
     peak_tf = peaks["bf16_tflops"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(f"{a.mode}|{B}|{H}x{W}")
     roofline = {
-        "kernel": "conv_tc_kernel (5x5 128->128 implicit GEMM, tcgen05)", "bound": "tensor",
-        "achieved": tfs, "peak": peak_tf, "unit": "TFLOP/s", "frac": tfs / peak_tf, "traffic": None,
+        "kernel": "conv_tc2_kernel<FUSE> (5x5 128->128 implicit GEMM + ReLU + fused 1x1 128->64, tcgen05 cta_group::2)",
+        "bound": "tensor",
+        "achieved": tfs, "peak": peak_tf, "unit": "TFLOP/s", "frac": tfs / peak_tf,
+        "traffic": traffic["bytes"] if traffic else None, "traffic_detail": traffic,
         "peak_source": peaks["source"] + ", dense bf16 burst" +
                        ("; tf32 runs at half the bf16 rate, so frac <= 0.5 in this mode" if a.mode == "tf32" else ""),
         "peak_for_this_dtype": peak_tf / 2 if a.mode == "tf32" else peak_tf,
