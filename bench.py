@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the other arithmetic modes")
+    ap.add_argument("--bundled", action="store_true",
+                    help="with --impl reference: BASELINE configs[0] -- the CPU forward over the 10 bundled Middlebury "
+                         "images (tests/golden/images) with the test.py loop semantics, printing name rmse ssim per image")
     return ap.parse_args()
 
 
@@ -163,10 +166,59 @@ def cpu_forward_sample(scale, height, width, budget_s, steps, warmup):
     return rows * width / 1e6 / mean_s, desc, cores, out, rows, mean_s
 
 
+def run_reference_bundled(a):
+    """BASELINE configs[0]: the reference's CPU path on the bundled images.  The .pth files are absent from the
+    reference checkout, so the weights are the synthetic seed-0 set (image quality is meaningless; the timing
+    and the pipeline are what is measured).  Loop semantics of CODON_X4/test.py:109-145."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import codon_oracle as orc
+    import cv2
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    img = os.path.join(ROOT, "tests", "golden", "images")
+    names = sorted(os.listdir(os.path.join(img, "gray")))
+    sd = orc.synthetic_state_dict(a.scale, 0)
+    rmse_sum = ssim_sum = 0.0
+    px = 0
+    t_fwd = 0.0
+    for n in names:
+        d = cv2.imread(os.path.join(img, f"depth_x{a.scale}", n), 0)
+        g = cv2.imread(os.path.join(img, "gray", n), 0)
+        lab = cv2.imread(os.path.join(img, "label", n), 0)
+        x = torch.from_numpy(d / 255).float()[None, None]
+        y = torch.from_numpy(g / 255).float()[None, None]
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            out = orc.forward(sd, x, y)[0, 0].numpy()
+        t_fwd += time.perf_counter() - t0
+        q = orc.quantise_output(out)
+        r, s_ = orc.masked_rmse(lab, q), orc.ssim_gauss(lab / 255, q / 255)
+        rmse_sum += r
+        ssim_sum += s_
+        px += d.size
+        print(n, r, s_, file=sys.stderr)
+    print(len(names), file=sys.stderr)
+    print(rmse_sum / len(names), ssim_sum / len(names), file=sys.stderr)
+    mps = px / 1e6 / t_fwd
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": mps, "unit": UNIT, "n_gpus": a.gpus,
+                      "steps": len(names), "warmup": 0, "ms_per_step": t_fwd / len(names) * 1e3, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "bundled Middlebury images, synthetic weights",
+                      "config": {"workload": f"BASELINE configs[0]: CODON x{a.scale} CPU forward over the 10 bundled images"},
+                      "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": "port",
+                                       "sample": f"{len(names)} bundled images, forward only, {cores} threads"},
+                      "mean_rmse": rmse_sum / len(names), "mean_ssim": ssim_sum / len(names),
+                      "e2e": {"value": mps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}), flush=True)
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if a.bundled:
+        return run_reference_bundled(a)
     steps, warmup = max(1, a.steps), max(0, a.warmup)
     mps, desc, cores, _, rows, mean_s = cpu_forward_sample(a.scale, a.height, a.width, 150.0, steps, warmup)
     line = {
@@ -337,6 +389,22 @@ def run_gpu(a):
                 variants[m] = {"value": P * k / 1e6 / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / k}
                 outs[m] = o2.clone()
                 e2.close()
+            # the same workload replayed from a CUDA graph (one graph launch instead of ~36 kernel launches)
+            try:
+                g = eng.capture_graph(B, H, W)
+                g.x.copy_(x); g.y.copy_(y)
+                for _ in range(3):
+                    g.replay()
+                torch.cuda.synchronize()
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+                for s_, e_ in ev:
+                    flush.zero_()
+                    s_.record(); g.replay(); e_.record()
+                torch.cuda.synchronize()
+                gms = sum(s_.elapsed_time(e_) for s_, e_ in ev)
+                variants[a.mode + "+cuda_graph"] = {"value": P * steps / 1e6 / (gms / 1e3), "unit": UNIT, "ms_per_step": gms / steps}
+            except Exception as exc:   # noqa: BLE001 - a variant, never the headline
+                variants[a.mode + "+cuda_graph"] = {"error": str(exc)[:200]}
             line["variants"] = variants
         else:
             outs = {a.mode: out.clone()}

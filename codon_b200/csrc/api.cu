@@ -905,4 +905,25 @@ int codon_ssim_gauss(const void* img1, const void* img2, int img_dtype, int B, i
   return CODON_OK;
 }
 
+int codon_bgr_to_gray_u8(const uint8_t* bgr, uint8_t* gray, size_t n_pixels, int method, void* cuda_stream) {
+  if (!bgr || !gray || method < 0 || method > 1) return fail(nullptr, CODON_ERR_ARG, "codon_bgr_to_gray_u8: bad argument");
+  if (n_pixels == 0) return CODON_OK;
+  CU_TRY(nullptr, launch_bgr_to_gray(bgr, gray, n_pixels, method, static_cast<cudaStream_t>(cuda_stream)));
+  return CODON_OK;
+}
+
+int codon_u8_to_unit_f32(const uint8_t* src, float* dst, size_t n, void* cuda_stream) {
+  if (!src || !dst) return fail(nullptr, CODON_ERR_ARG, "codon_u8_to_unit_f32: NULL pointer");
+  if (n == 0) return CODON_OK;
+  CU_TRY(nullptr, launch_u8_to_unit(src, dst, n, static_cast<cudaStream_t>(cuda_stream)));
+  return CODON_OK;
+}
+
+int codon_bicubic_upsample_f32(const float* src, float* dst, int B, int h, int w, int H, int W, void* cuda_stream) {
+  if (!src || !dst || B < 1 || h < 1 || w < 1 || H < 1 || W < 1)
+    return fail(nullptr, CODON_ERR_ARG, "codon_bicubic_upsample_f32: bad argument");
+  CU_TRY(nullptr, launch_bicubic_up(src, dst, B, h, w, H, W, static_cast<cudaStream_t>(cuda_stream)));
+  return CODON_OK;
+}
+
 }  // extern "C"

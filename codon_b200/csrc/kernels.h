@@ -84,6 +84,11 @@ size_t ssim_workspace_bytes(int B, int H, int W);
 cudaError_t launch_ssim_gauss(const void* a, const void* b, int img_dtype, int B, int H, int W, double sd, double c1, double c2,
                               double* ssim, double* ws, cudaStream_t st);
 
+// ---- driver pre-processing (preproc.cu) ------------------------------------------------------------
+cudaError_t launch_bgr_to_gray(const uint8_t* bgr, uint8_t* gray, size_t n, int method, cudaStream_t st);
+cudaError_t launch_u8_to_unit(const uint8_t* src, float* dst, size_t n, cudaStream_t st);
+cudaError_t launch_bicubic_up(const float* src, float* dst, int B, int h, int w, int H, int W, cudaStream_t st);
+
 // ---- tcgen05 implicit-GEMM convolution (BF16 / FP16 / TF32 modes), conv_tc.cu -------------------
 struct TcConvPlan;   // defined in conv_tc.h
 

@@ -27,6 +27,7 @@ ABI_SYMBOLS = [
     "codon_profile_reset", "codon_profile_category_name", "codon_cac_channel", "codon_cac_spatial",
     "codon_cac_apply", "codon_channel_stats", "codon_channel_pool", "codon_conv2d_nchw",
     "codon_masked_rmse", "codon_ssim_gauss", "codon_quantise_u8",
+    "codon_bgr_to_gray_u8", "codon_u8_to_unit_f32", "codon_bicubic_upsample_f32",
 ]
 
 _lib = None
@@ -80,6 +81,9 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         lib.codon_masked_rmse.argtypes = [vp, vp, ip, ip, ip, vp, vp]
         lib.codon_ssim_gauss.argtypes = [vp, vp, ip, ip, ip, ip, c.c_double, c.c_double, c.c_double, vp, vp, c.c_size_t, vp]
         lib.codon_quantise_u8.argtypes = [vp, vp, c.c_size_t, ip, vp]
+        lib.codon_bgr_to_gray_u8.argtypes = [vp, vp, c.c_size_t, ip, vp]
+        lib.codon_u8_to_unit_f32.argtypes = [vp, vp, c.c_size_t, vp]
+        lib.codon_bicubic_upsample_f32.argtypes = [vp, vp, ip, ip, ip, ip, ip, vp]
         for name in ABI_SYMBOLS:
             fn = getattr(lib, name)
             if name not in ("codon_destroy", "codon_last_error", "codon_version", "codon_workspace_bytes",
@@ -203,6 +207,11 @@ class Engine:
             check(self.lib.codon_forward_host(self._ctx, d.ctypes.data, g.ctypes.data, out.ctypes.data, B, H, W), self._ctx)
         return out
 
+    def capture_graph(self, B: int, H: int, W: int, dtype: torch.dtype = torch.float32) -> "GraphedForward":
+        """Captures the forward for a fixed shape into a CUDA graph: one
+        cudaGraphLaunch replaces the ~36 kernel launches of a frame."""
+        return GraphedForward(self, B, H, W, dtype)
+
     @property
     def last_launch_count(self) -> int:
         return int(self.lib.codon_last_launch_count(self._ctx))
@@ -231,6 +240,42 @@ class Engine:
             check(self.lib.codon_debug_tap(self._ctx, name.encode(), dst.data_ptr(), ctypes.byref(c),
                                            current_stream_ptr(self.device)), self._ctx)
         return dst
+
+
+class GraphedForward:
+    """A CUDA-graph replay of ``Engine.forward`` for one (B, H, W, dtype).  The library's launches are
+    stream-ordered and allocation-free (the workspace is caller-owned), so the whole forward is
+    capturable; inputs are copied into static buffers before each replay."""
+
+    def __init__(self, eng: "Engine", B: int, H: int, W: int, dtype: torch.dtype = torch.float32):
+        self.eng = eng
+        dev = eng.device
+        self.x = torch.zeros(B, 1, H, W, dtype=dtype, device=dev)
+        self.y = torch.zeros(B, 1, H, W, dtype=dtype, device=dev)
+        self.out = torch.empty(B, 1, H, W, dtype=dtype, device=dev)
+        eng.profile_enable(False)
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):                      # warm-up: function attributes, tensor maps, workspace
+                    eng.forward(self.x, self.y, self.out)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                eng.forward(self.x, self.y, self.out)
+
+    def __call__(self, depth: torch.Tensor, guide: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(depth.reshape(self.x.shape))
+        self.y.copy_(guide.reshape(self.y.shape))
+        self.graph.replay()
+        return self.out
+
+    def replay(self) -> torch.Tensor:
+        """Replays on the data already in ``self.x`` / ``self.y``."""
+        self.graph.replay()
+        return self.out
 
 
 # ---- stand-alone attention pieces (module-level API of CAC_module / attention.ResCBAM) -------------
@@ -388,3 +433,46 @@ def ssim_gauss(img1: torch.Tensor, img2: torch.Tensor, sd: float = 1.5, c1: floa
         check(lib.codon_ssim_gauss(a.data_ptr(), b.data_ptr(), dt, B, H, W, sd, c1, c2, r.data_ptr(), ws.data_ptr(),
                                    ws.numel() * 8, current_stream_ptr(a.device)))
     return r
+
+
+# ---- driver pre-processing on the GPU ----------------------------------------------------------------
+
+def bgr_to_gray_u8(bgr: torch.Tensor, method: str = "imread") -> torch.Tensor:
+    """uint8 [..., H, W, 3] (BGR, as cv2 decodes) -> uint8 [..., H, W].  method "imread": what
+    cv2.imread(png, 0) returns (libpng conversion, test.py:118); "cvtcolor": cv2.cvtColor(BGR2GRAY)."""
+    lib = load_library()
+    _require_cuda(bgr, "bgr")
+    if bgr.dtype != torch.uint8 or bgr.shape[-1] != 3:
+        raise CodonError("bgr_to_gray_u8 needs a uint8 [..., 3] tensor")
+    src = bgr.contiguous()
+    dst = torch.empty(src.shape[:-1], dtype=torch.uint8, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib.codon_bgr_to_gray_u8(src.data_ptr(), dst.data_ptr(), dst.numel(), {"imread": 0, "cvtcolor": 1}[method],
+                                       current_stream_ptr(src.device)))
+    return dst
+
+
+def u8_to_unit_f32(img: torch.Tensor) -> torch.Tensor:
+    """uint8 -> float32(v / 255) (CODON_X4/test.py:122-123)."""
+    lib = load_library()
+    _require_cuda(img, "img")
+    if img.dtype != torch.uint8:
+        raise CodonError("u8_to_unit_f32 needs a uint8 tensor")
+    src = img.contiguous()
+    dst = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib.codon_u8_to_unit_f32(src.data_ptr(), dst.data_ptr(), src.numel(), current_stream_ptr(src.device)))
+    return dst
+
+
+def bicubic_upsample(lr: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """float32 [B,h,w] (or [B,1,h,w]) -> [B,H,W] with cv2.resize(INTER_CUBIC) semantics."""
+    lib = load_library()
+    src = _f32c(lr, "lr")
+    shp = src.shape
+    src = src.reshape(-1, shp[-2], shp[-1])
+    B, h, w = src.shape
+    dst = torch.empty(B, H, W, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib.codon_bicubic_upsample_f32(src.data_ptr(), dst.data_ptr(), B, h, w, H, W, current_stream_ptr(src.device)))
+    return dst.reshape(*shp[:-2], H, W)

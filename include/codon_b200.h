@@ -173,6 +173,19 @@ int codon_ssim_gauss(const void* img1, const void* img2, int img_dtype, int B, i
                      double c1, double c2, double* ssim, void* workspace, size_t workspace_bytes,
                      void* cuda_stream);
 
+/* ---- driver pre-processing on the GPU (DEVICE pointers) ------------------------------------------
+ * Replaces the colour -> gray conversion of cv2.imread(path, 0) (CODON_X4/test.py:118) for an already decoded
+ * 8-bit BGR image [n_pixels, 3].  method 0: what imread(.., 0) yields for a colour PNG (libpng's
+ * rgb_to_gray, (R*9797 + G*19234 + B*3737) >> 15); method 1: cv2.cvtColor BGR2GRAY
+ * ((B*1868 + G*9617 + R*4899 + 8192) >> 14). */
+int codon_bgr_to_gray_u8(const uint8_t* bgr, uint8_t* gray, size_t n_pixels, int method, void* cuda_stream);
+/* Replaces torch.from_numpy(img / 255).float() (test.py:122-123): dst[i] = float32(double(src[i]) / 255). */
+int codon_u8_to_unit_f32(const uint8_t* src, float* dst, size_t n, void* cuda_stream);
+/* The pre-upsampling of the low-resolution depth that the reference leaves to an unshipped offline step
+ * (test.py:77 "Bicubic/X4"): src [B,h,w] -> dst [B,H,W] fp32 with the semantics of
+ * cv2.resize(src, (W, H), interpolation=cv2.INTER_CUBIC) (a = -0.75, half-pixel centres, replicated border). */
+int codon_bicubic_upsample_f32(const float* src, float* dst, int B, int h, int w, int H, int W, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ cannot travel to the GPU box, so its outputs on fixed inputs are committed as fi
   tests/golden/images/        the bundled Middlebury inputs as read by test.py:116-118
                               (cv2.imread(path, 0) -> single-channel uint8 PNG), labels and the
                               authors' x4/x8/x16 outputs (data, not code)
+  tests/golden/preproc.npz    cv2 gray conversion of a colour crop; cv2.resize(INTER_CUBIC) of LR depth crops
   tests/golden/metrics.json   EvaluationResults (test.py:148-164, exec'd from source lines) and
                               ssim_2.ssim_exact on those images
 
@@ -158,3 +159,30 @@ if __name__ == "__main__":
     run_forward(16, 2, (1, 64, 80), "x16_s2_b1_64x80", 99)
     run_forward(4, 0, (1, 120, 160), "x4_s0_b1_120x160", 4321)
     run_image_forward(4, 0, "Tsukuba.png", "x4_s0_tsukuba")
+    run_preproc()
+
+
+def run_preproc():
+    """Fixtures for the GPU pre-processing kernels: cv2's own gray conversion of a decoded colour image
+    (what cv2.imread(path, 0) returns, test.py:118) and cv2.resize(INTER_CUBIC) on float32."""
+    import cv2
+    col = cv2.imread(os.path.join(REF, "CODON_X4", "input_color", "Art.png"), cv2.IMREAD_COLOR)
+    gray = cv2.imread(os.path.join(REF, "CODON_X4", "input_color", "Art.png"), 0)
+    r, g, b = (col[..., i].astype(np.uint32) for i in (2, 1, 0))
+    libpng = ((r * 9797 + g * 19234 + b * 3737) >> 15).astype(np.uint8)       # png_set_rgb_to_gray(0.299, 0.587)
+    cvt = cv2.cvtColor(col, cv2.COLOR_BGR2GRAY)
+    print("imread(path,0) == libpng formula on imread(path,1):", bool((libpng == gray).all()))
+    y0, x0 = 100, 150
+    bgr_crop = np.ascontiguousarray(col[y0:y0 + 64, x0:x0 + 80])
+    gray_crop = np.ascontiguousarray(gray[y0:y0 + 64, x0:x0 + 80])
+    dep = cv2.imread(os.path.join(REF, "CODON_X4", "input_label", "Art.png"), 0)
+    out = {"bgr": bgr_crop, "gray": gray_crop, "gray_cvtcolor": np.ascontiguousarray(cvt[y0:y0 + 64, x0:x0 + 80])}
+    for s, (H, W) in ((4, (92, 116)), (8, (120, 88)), (16, (97, 131))):
+        hr = dep[40:40 + H, 60:60 + W].astype(np.float32) / 255
+        h, w = max(1, H // s), max(1, W // s)
+        lr = cv2.resize(hr, (w, h), interpolation=cv2.INTER_AREA)
+        up = cv2.resize(lr, (W, H), interpolation=cv2.INTER_CUBIC)
+        out[f"lr_x{s}"] = lr
+        out[f"up_x{s}"] = up
+    np.savez_compressed(os.path.join(GOLD, "preproc.npz"), **out)
+    print("preproc fixtures written")

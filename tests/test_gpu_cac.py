@@ -115,3 +115,21 @@ def test_quantise_matches_driver_rule():
     h = a.astype(np.float16)
     got_h = engine.quantise_u8(torch.from_numpy(a).cuda(), via_half=True).cpu().numpy()
     np.testing.assert_array_equal(got_h, orc.quantise_output(h))
+
+
+def test_gpu_preprocessing_matches_cv2_fixtures(golden_dir):
+    """BGR->gray (cv2.imread(path, 0) arithmetic), /255 normalisation, bicubic pre-upsampling
+    (cv2.resize INTER_CUBIC on float32) against fixtures generated with cv2 (oracle/make_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "preproc.npz"))
+    gray = engine.bgr_to_gray_u8(torch.from_numpy(g["bgr"]).cuda())
+    np.testing.assert_array_equal(gray.cpu().numpy(), g["gray"])
+    np.testing.assert_array_equal(engine.bgr_to_gray_u8(torch.from_numpy(g["bgr"]).cuda(), "cvtcolor").cpu().numpy(),
+                                  g["gray_cvtcolor"])
+    unit = engine.u8_to_unit_f32(gray)
+    np.testing.assert_array_equal(unit.cpu().numpy(), (g["gray"] / 255).astype(np.float32))
+    for s in (4, 8, 16):
+        lr, up = g[f"lr_x{s}"], g[f"up_x{s}"]
+        got = engine.bicubic_upsample(torch.from_numpy(lr).cuda()[None], up.shape[0], up.shape[1])[0].cpu().numpy()
+        err = np.abs(got - up).max()
+        print(f"bicubic x{s}: max err vs cv2 {err:.2e}")
+        assert err <= 2e-6

@@ -159,3 +159,20 @@ def test_full_size_linearity_property_free_checks():
     net.load_state_dict(sd0)
     with torch.no_grad():
         assert torch.equal(net(xc, yc), xc)
+
+
+def test_cuda_graph_replay_is_bit_exact():
+    """The whole forward is capturable into a CUDA graph (no allocation, no sync inside codon_forward)."""
+    sd = orc.synthetic_state_dict(4, 0)
+    x, y = orc.synthetic_frames(1, 96, 176, 21)
+    x2, y2 = orc.synthetic_frames(1, 96, 176, 22)
+    for mode in ("bf16", "tf32"):
+        net = _net(4, 0, mode)
+        eng = net.engine(torch.device("cuda", 0))
+        with torch.no_grad():
+            direct = eng.forward(x.cuda(), y.cuda()).clone()
+            direct2 = eng.forward(x2.cuda(), y2.cuda()).clone()
+        g = eng.capture_graph(1, 96, 176)
+        assert torch.equal(g(x.cuda(), y.cuda()), direct)
+        assert torch.equal(g(x2.cuda(), y2.cuda()), direct2)
+        assert torch.equal(g(x.cuda(), y.cuda()), direct)
