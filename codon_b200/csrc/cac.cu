@@ -181,37 +181,48 @@ __global__ void __launch_bounds__(256, 4) cac_chan_stats_kernel(const T* __restr
 
 // One CTA per frame, 1024 threads.  F channel c (depth 0..63 | colour 64..127) is Fcat channel
 // (c + 64) % 128 (Fcat = [colour | depth], CODON_x4.py:85); w1 is indexed by Fcat channel.
-// The chunk partials are reduced in a fixed order (4 interleaved lanes per column, then a fixed
-// 4-way combine), so the result does not depend on the batch size or the GPU count.
+// The chunk partials ([chunks][sum 128 | max 128]) are reduced in a fixed order -- 16 interleaved groups of
+// chunks, each thread one float4 of columns, then a fixed 16-way combine -- so the result does not depend
+// on the batch size or the GPU count.
 __global__ void __launch_bounds__(1024) cac_mlp_kernel(const float* __restrict__ part, int chunks, int HW,
                                                        const float* __restrict__ w1,
                                                        const float* __restrict__ b1,
                                                        const float* __restrict__ w2,
                                                        const float* __restrict__ b2,
                                                        float* __restrict__ sc) {
-  __shared__ float red[4][256], avg[128], mx[128], hid[2][8];
-  const int b = blockIdx.x, t = threadIdx.x, col = t & 255, grp = t >> 8;
-  const float* src = part + (size_t)b * chunks * 256;
-  const bool is_max = col >= 128;
-  float acc = is_max ? -INFINITY : 0.f;
-  for (int c0 = grp; c0 < chunks; c0 += 32) {        // 8 independent loads in flight, combined in a fixed order
-    float v[8];
+  __shared__ float4 red[16][64];
+  __shared__ float avg[128], mx[128], hid[2][8];
+  const int b = blockIdx.x, t = threadIdx.x, cg = t & 63, grp = t >> 6;
+  const float4* src = reinterpret_cast<const float4*>(part + (size_t)b * chunks * 256) + cg;
+  const bool is_max = cg >= 32;                  // float4 columns 32..63 hold the per-channel maxima
+  float4 acc = is_max ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c0 = grp; c0 < chunks; c0 += 16 * 8) {     // 8 independent 16-byte loads in flight per thread
+    float4 v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int c = c0 + 4 * u;
-      v[u] = c < chunks ? src[(size_t)c * 256 + col] : (is_max ? -INFINITY : 0.f);
+      const int c = c0 + 16 * u;
+      v[u] = c < chunks ? __ldg(src + (size_t)c * 64) : acc;
+      if (c >= chunks) v[u] = is_max ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc = is_max ? fmaxf(acc, v[u]) : acc + v[u];
+    for (int u = 0; u < 8; ++u) {
+      if (is_max) { acc.x = fmaxf(acc.x, v[u].x); acc.y = fmaxf(acc.y, v[u].y); acc.z = fmaxf(acc.z, v[u].z); acc.w = fmaxf(acc.w, v[u].w); }
+      else { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
   }
-  red[grp][col] = acc;
+  red[grp][cg] = acc;
   __syncthreads();
   if (t < 256) {
-    float r = red[0][t];
+    const int col = t, q4 = col >> 2, e = col & 3;
+    const bool mxcol = col >= 128;
+    float r = reinterpret_cast<const float*>(&red[0][q4])[e];
 #pragma unroll
-    for (int g = 1; g < 4; ++g) r = is_max ? fmaxf(r, red[g][t]) : r + red[g][t];
-    const int fc = ((t & 127) + 64) & 127;
-    if (is_max) mx[fc] = r; else avg[fc] = r / (float)HW;
+    for (int g = 1; g < 16; ++g) {
+      const float v = reinterpret_cast<const float*>(&red[g][q4])[e];
+      r = mxcol ? fmaxf(r, v) : r + v;
+    }
+    const int fc = ((col & 127) + 64) & 127;
+    if (mxcol) mx[fc] = r; else avg[fc] = r / (float)HW;
   }
   __syncthreads();
   if (t < 512) {

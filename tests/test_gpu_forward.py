@@ -176,3 +176,28 @@ def test_cuda_graph_replay_is_bit_exact():
         assert torch.equal(g(x.cuda(), y.cuda()), direct)
         assert torch.equal(g(x2.cuda(), y2.cuda()), direct2)
         assert torch.equal(g(x.cuda(), y.cuda()), direct)
+
+
+def test_1080p_x16_in_kernel_tiling_properties():
+    """BASELINE config 4 shape (x16 class, 1920x1080): the in-kernel halo tiling covers ~8000 tiles per launch.
+    Size-independent checks: finite, deterministic, batch-invariant (a frame alone == the same frame inside a
+    batch, bit-exact: the CAC reductions are per frame and fixed-order), and the 16-bit / tf32 modes agree
+    within the fp32-parity tolerance."""
+    sd = orc.synthetic_state_dict(16, 2)
+    x, y = orc.synthetic_frames(2, 1080, 1920, 3)
+    xc, yc = x.cuda(), y.cuda()
+    outs = {}
+    for mode in ("tf32", "fp16"):
+        net = CODON_x16.CODONNet().eval().set_mode(mode)
+        net.load_state_dict(sd)
+        with torch.no_grad():
+            both = net(xc, yc).clone()
+            single = net(xc[1:2], yc[1:2]).clone()
+            again = net(xc, yc).clone()
+        assert torch.isfinite(both).all()
+        assert torch.equal(both, again)
+        assert torch.equal(both[1:2], single)
+        outs[mode] = both
+    err = float((outs["tf32"] - outs["fp16"]).abs().max())
+    print(f"1080p x16 tf32 vs fp16: {err:.3e}")
+    assert err <= 1e-3
