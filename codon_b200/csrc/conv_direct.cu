@@ -9,6 +9,7 @@
 // the weights of all taps are staged in shared memory KC = 8 input channels at a time;
 // A operands are broadcast 128-bit loads, B operands conflict-free 128-bit loads
 // (16 LDS.128 per 256 FFMA).
+#include <atomic>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -125,12 +126,15 @@ template <int KS>
 cudaError_t launch_ks(const DirectParams& p, int njobs, cudaStream_t st) {
   constexpr int PH = kTH + KS - 1, PW = kTW + KS - 1, T = KS * KS;
   const size_t smem = sizeof(float) * (PH * PW * kKC + T * kKC * kNC);
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<int> configured[64];      // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!configured[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(conv_direct_f32_kernel<KS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev].store(1, std::memory_order_release);
   }
   dim3 grid(p.tiles_x * cdiv(p.H, kTH), p.nchunks * njobs, p.B);
   conv_direct_f32_kernel<KS><<<grid, 128, smem, st>>>(p);

@@ -30,6 +30,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <cmath>
+#include <atomic>
 #include "common.cuh"
 #include "kernels.h"
 #include "conv_tc.h"
@@ -38,6 +39,7 @@ namespace codon {
 
 namespace {
 
+constexpr int kMaxDevices = 64;
 constexpr int kMaxNPB = 8;                     // patch stages: as many as fit (runtime, TcKParams::npb)
 constexpr int kBStages = 4;
 constexpr uint32_t kBStageBytes = 128 * 128;   // up to 128 rows x 128 B
@@ -1103,15 +1105,17 @@ size_t setup_geometry(TcKParams& kp, int b_stage_bytes_total) {
 template <int NACC, int OPERAND, bool FUSE>
 cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, const CUtensorMap& b0, const CUtensorMap& b1,
                          const CUtensorMap& w0, const CUtensorMap& w1, TcKParams& kp, cudaStream_t st) {
-  static bool configured = false;
-  static int num_sms = 0;
-  if (!configured) {
+  // function attributes are per device: configure once per (kernel instantiation, device); one host thread per GPU
+  static std::atomic<int> sms_of_dev[kMaxDevices];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  int num_sms = sms_of_dev[dev].load(std::memory_order_acquire);
+  if (num_sms == 0) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NACC, OPERAND, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
+    sms_of_dev[dev].store(num_sms, std::memory_order_release);
   }
   // fused mode adds the resident 1x1 weights (16 KB) and the Y staging tile (32 KB) behind the B ring
   const size_t smem = setup_geometry<NACC>(kp, kB2Stages * kB2StageBytes + (FUSE ? 49152 : 0));
@@ -1131,15 +1135,16 @@ cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, con
 
 template <int NACC, int OPERAND>
 cudaError_t launch_nacc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, TcKParams& kp, cudaStream_t st) {
-  static bool configured = false;
-  static int num_sms = 0;
-  if (!configured) {
+  static std::atomic<int> sms_of_dev[kMaxDevices];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  int num_sms = sms_of_dev[dev].load(std::memory_order_acquire);
+  if (num_sms == 0) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<NACC, OPERAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
+    sms_of_dev[dev].store(num_sms, std::memory_order_release);
   }
   const size_t smem = setup_geometry<NACC>(kp, kBStages * kBStageBytes);
   if (!smem) return cudaErrorInvalidConfiguration;

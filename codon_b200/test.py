@@ -11,7 +11,7 @@ checkpoint name (:56) and is broken as shipped; here they are fl
   --scale {4,8,16}   which CODONNet (default 4)          --mode fp16|bf16|tf32|fp32 (default fp16 = .half())
   --input-depth DIR  pre-upsampled depth PNGs             --input-color DIR   guide images
   --label DIR        ground truth                         --fix DIR           hole-filled GT for SSIM (default: label)
-  --out DIR          result PNGs (default CODON_result_save/)   --log FILE    tee of stdout (default ./test_sintel.txt)
+  --out DIR          result PNGs (default CODON_result_save/)   --logfile F   tee of stdout (default ./test_sintel.txt)
   --pretrained FILE  X4.pth-style checkpoint; without it seeded synthetic weights are used (and said so)
 
 Everything between the PNG decode and the PNG encode runs on the GPU (forward, quantisation, RMSE,
@@ -46,7 +46,7 @@ parser.add_argument("--input-color", default=None)
 parser.add_argument("--label", default=None)
 parser.add_argument("--fix", default=None)
 parser.add_argument("--out", default="CODON_result_save/")
-parser.add_argument("--log", default="./test_sintel.txt")
+parser.add_argument("--logfile", default="./test_sintel.txt", help="tee of stdout (reference: ./test_sintel.txt); empty = none")
 parser.add_argument("--seed", type=int, default=None)
 parser.add_argument("--weights-seed", type=int, default=0, help="seed of the synthetic weights used without --pretrained")
 
@@ -166,8 +166,8 @@ def main(argv=None):
     print("===> Building model")
     model = _build_model(opt.scale)                                                      # test.py:48
     model.set_mode(opt.mode)
-    if opt.log:
-        sys.stdout = Logger(opt.log)                                                     # test.py:53
+    if opt.logfile and int(os.environ.get("RANK", "0")) == 0:
+        sys.stdout = Logger(opt.logfile)                                                     # test.py:53
     if opt.pretrained:
         from .checkpoint import load_checkpoint
         sd, meta = load_checkpoint(opt.pretrained)                                       # test.py:56-59

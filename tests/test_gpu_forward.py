@@ -201,3 +201,26 @@ def test_1080p_x16_in_kernel_tiling_properties():
     err = float((outs["tf32"] - outs["fp16"]).abs().max())
     print(f"1080p x16 tf32 vs fp16: {err:.3e}")
     assert err <= 1e-3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpus_one_process_same_bits():
+    """Frame sharding over GPUs in one process (one host thread per GPU): every GPU produces
+    the same bits for the same frame, concurrently."""
+    from codon_b200 import scheduler as sch
+    sd = orc.synthetic_state_dict(4, 0)
+    x, y = orc.synthetic_frames(4, 130, 170, 9)
+    net = _net(4, 0, "bf16")
+    with torch.no_grad():
+        ref = net(x.cuda(0), y.cuda(0)).cpu()
+
+    def run(gpu, i):
+        dev = torch.device("cuda", gpu)
+        with torch.no_grad():
+            o = net.engine(dev).forward(x[i:i + 1].to(dev), y[i:i + 1].to(dev))
+        torch.cuda.synchronize(dev)
+        return o.cpu()
+
+    outs = sch.MultiGpuExecutor([0, 1]).map(run, list(range(4)))
+    for i, o in enumerate(outs):
+        assert torch.equal(o, ref[i:i + 1])

@@ -69,7 +69,7 @@ def test_driver_end_to_end_on_bundled_images(golden_dir, tmp_path, capsys):
     out_dir = tmp_path / "CODON_result_save"
     res = driver.main(["--gpus", "0", "--scale", "4", "--mode", "fp16", "--input-depth", os.path.join(img, "depth_x4"),
                        "--input-color", os.path.join(img, "gray"), "--label", os.path.join(img, "label"),
-                       "--out", str(out_dir) + "/", "--log", str(tmp_path / "log.txt"), "--seed", "1"])
+                       "--out", str(out_dir) + "/", "--logfile", str(tmp_path / "log.txt"), "--seed", "1"])
     import sys
     sys.stdout = sys.__stdout__
     mean_rmse, mean_ssim, n = res
