@@ -19,7 +19,10 @@
 #include <cstring>
 #include <cstdlib>
 #include <map>
+#include <atomic>
 #include <mutex>
+#include <thread>
+#include <chrono>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -59,6 +62,7 @@ struct Buffers {
   // byte offsets into the workspace
   size_t xf = 0, yf = 0, of32 = 0, E = 0, F = 0, MS = 0, R2 = 0, FUSE = 0, OF = 0, pooled = 0, part = 0, sc = 0;
   size_t total = 0;
+  size_t px = 0;      // pixels the layout was planned for (B*H*W; the band mode plans every GPU for the tallest band)
   int chunks = 0;
 };
 
@@ -151,9 +155,10 @@ struct ProfScope {
   ~ProfScope() { if (b) cudaEventRecord(b, st); }
 };
 
-Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W) {
+Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W, int part_chunks = 0) {
   Buffers b;
   const size_t P = (size_t)B * H * W, e = act_bytes(ctx->act);
+  b.px = P;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   b.xf = take(P * 4); b.yf = take(P * 4); b.of32 = take(P * 4);
@@ -162,7 +167,7 @@ Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W) {
   b.FUSE = take(P * 64 * e); b.OF = take(P * 64 * e);
   b.pooled = take(P * 2 * 4 * 4);   // (max, mean) map, or 2 / 4 (max, sum) partial maps from the 1x1 epilogues
   b.chunks = cac_stats_chunks(B, H, W);
-  b.part = take((size_t)B * b.chunks * 256 * 4);
+  b.part = take((size_t)B * (part_chunks > b.chunks ? part_chunks : b.chunks) * 256 * 4);
   b.sc = take((size_t)B * 64 * 4);
   b.total = off + 1024;   // slack for aligning the caller's pointer
   return b;
@@ -234,11 +239,27 @@ int use_two_cta(int B, int H, int W, int nacc) {
   return tiles >= 148 ? 1 : 0;
 }
 
+// Row-band mode (codon_group_*): one frame is split into horizontal bands, one per GPU.  Each band keeps
+// kBandHalo extra rows on its interior sides; after every layer the hook refreshes those rows from the
+// neighbouring GPUs' core rows over NVLink peer memory, and the per-band CAC channel partials are
+// all-gathered so that every GPU evaluates the same gate MLP.
+constexpr int kBandHalo = 2;
+struct BandHook {
+  int cy0 = 0, cy1 = 0;             // core rows [cy0, cy1) of the local image
+  long global_hw = 0;               // pixels of the whole frame (the average pool divides by it)
+  int chunk_off = 0, chunks_total = 0;   // this band's slot in / the size of the gathered partial buffer
+  virtual int halo(const size_t* off, const size_t* row_bytes, int n) = 0;
+  virtual int gather_parts(size_t part_off) = 0;
+  virtual ~BandHook() {}
+};
+
 // One conv layer of the plan: up to two jobs reading channel slices of `in` (in_C channels).
 struct LayerJob { const char* w; int in_off; size_t out; int out_stride, out_off; size_t res; int res_stride, res_off; bool has_res; size_t pool = 0; bool has_pool = false; size_t in_add = 0; };
 
 struct Runner {
   codon_ctx* ctx; uint8_t* ws; int B, H, W; cudaStream_t st; int e;
+  int Hdec;          // height the kernel-variant decisions are based on (band mode: identical on every GPU)
+  size_t px;         // planned pixels (Buffers::px): stride of the per-branch halves and of the pool partial maps
 
   int conv(const char* plan_name, size_t in, int in_C, int cin, int cout, int ks, bool relu,
            const LayerJob* jobs, int njobs) {
@@ -261,7 +282,7 @@ struct Runner {
     const TcLayer& l0 = ctx->w_tc.at(jobs[0].w);
     TcLaunch L;
     L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = relu; L.out_act = ctx->act;
-    L.nacc = pick_nacc(B, H, W, njobs, ks == 5 ? 2 : 4, "CODON_TC_NACC_CONV");
+    L.nacc = pick_nacc(B, Hdec, W, njobs, ks == 5 ? 2 : 4, "CODON_TC_NACC_CONV");
     for (int i = 0; i < njobs; ++i) {
       const TcLayer& l = ctx->w_tc.at(jobs[i].w);
       L.job[i].in_coff = jobs[i].in_off;
@@ -279,7 +300,7 @@ struct Runner {
       if (all < 0) { const char* e = getenv("CODON_TC_2CTA_ALL"); all = e ? atoi(e) : 0; }
       // cluster mode: the 5x5 layers (+15-20 %) and, with one patch per slab, the 3x3 layers (+30 %); the
       // stand-alone 1x1 (fallback path only) stays single-CTA: its epilogue emits the ChannelPool partials
-      L.two_cta = (ks == 5 || ks == 3 || (all && !jobs[0].has_pool)) ? use_two_cta(B, H, W, L.nacc) : 0;
+      L.two_cta = (ks == 5 || ks == 3 || (all && !jobs[0].has_pool)) ? use_two_cta(B, Hdec, W, L.nacc) : 0;
     }
     const CUtensorMap* tm[2] = {nullptr, nullptr};
     for (int i = 0; i < njobs; ++i) {
@@ -301,12 +322,12 @@ struct Runner {
     static int env = -2;
     if (env == -2) { const char* e = getenv("CODON_TC_FUSE"); env = e ? atoi(e) : 1; }
     if (ctx->mode == CODON_MODE_FP32 || !env) return 1;
-    const int nacc = pick_nacc(B, H, W, njobs, 2, "CODON_TC_NACC_CONV");
-    if (nacc > 2 || !use_two_cta(B, H, W, nacc)) return 1;
+    const int nacc = pick_nacc(B, Hdec, W, njobs, 2, "CODON_TC_NACC_CONV");
+    if (nacc > 2 || !use_two_cta(B, Hdec, W, nacc)) return 1;
     const TcLayer& l0 = ctx->w_tc.at(jobs[0].w5);
     TcLaunch L;
     L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = 1; L.out_act = ctx->act;
-    L.nacc = nacc; L.two_cta = 1; L.fuse = 1;
+    L.nacc = nacc; L.two_cta = 1; L.fuse = 1; L.pool_stride = px;
     L.y16_operand = ctx->mode == CODON_MODE_BF16 ? TC_BF16 : TC_F16;
     const CUtensorMap* tm[2] = {nullptr, nullptr};
     for (int i = 0; i < njobs; ++i) {
@@ -362,7 +383,7 @@ struct Runner {
     const TcLayer& l0 = ctx->w_tc.at(wpair[0]);
     TcLaunch L;
     L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = 1; L.out_act = ctx->act;
-    L.nacc = pick_nacc(B, H, W, njobs, 2, "CODON_TC_NACC_PAIR");
+    L.nacc = pick_nacc(B, Hdec, W, njobs, 2, "CODON_TC_NACC_PAIR");
     for (int i = 0; i < njobs; ++i) {
       const TcLayer& l = ctx->w_tc.at(wpair[i]);
       L.job[i].in_coff = in_off[i];
@@ -373,7 +394,7 @@ struct Runner {
       L.job[i].pool = nullptr;
       L.bmap[i] = &l.bmap;
     }
-    L.two_cta = use_two_cta(B, H, W, L.nacc);
+    L.two_cta = use_two_cta(B, Hdec, W, L.nacc);
     const CUtensorMap* tm = nullptr;
     int rc = get_tmap(ctx, ws + in, in_C, tc_box_w(l0.plan, L.nacc), tc_box_h(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
     if (rc) return rc;
@@ -385,12 +406,20 @@ struct Runner {
 };
 
 int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int B, int H, int W, uint8_t* ws,
-                const Buffers& bf, cudaStream_t st) {
-  Runner r{ctx, ws, B, H, W, st, act_bytes(ctx->act)};
+                const Buffers& bf, cudaStream_t st, BandHook* hook = nullptr) {
+  Runner r{ctx, ws, B, H, W, st, act_bytes(ctx->act), hook ? (int)(bf.px / (size_t)W) : H, bf.px};
+  // band mode: refresh the halo rows of the buffers a layer wrote (no-op otherwise)
+  auto halo = [&](std::initializer_list<size_t> offs, int channels_or_bytes, bool raw_bytes = false) -> int {
+    if (!hook) return CODON_OK;
+    size_t o[4], rb[4];
+    int n = 0;
+    for (size_t v : offs) { o[n] = v; rb[n] = raw_bytes ? (size_t)W * channels_or_bytes : (size_t)W * channels_or_bytes * r.e; ++n; }
+    return hook->halo(o, rb, n);
+  };
   const bool tc_mode = ctx->mode != CODON_MODE_FP32;
   // MS and R2 hold the depth branch in their first half and the colour branch in the second (128 channels
   // each, pixel-contiguous per branch: a branch's 256/512-byte pixel rows are read and written whole)
-  const size_t half = (size_t)B * H * W * 128 * r.e;
+  const size_t half = bf.px * 128 * r.e;
   int rc;
   // encoders (CODON_x4.py:68-73): input/input_c 1->64 (+ReLU) into the R2 region viewed as 128 ch
   const size_t T0 = bf.R2;
@@ -400,10 +429,12 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     CU_TRY(ctx, launch_conv_first(x, y, ctx->w_in_d, ctx->w_in_c, ws + T0, ctx->act, B, H, W, st, ctx->mode == CODON_MODE_TF32));
   }
   ctx->launches++;
+  if ((rc = halo({T0}, 128))) return rc;
   {
     LayerJob j[2] = {{"conv_input", 0, bf.E, 128, 0, 0, 0, 0, false}, {"conv_input_c", 64, bf.E, 128, 64, 0, 0, 0, false}};
     if ((rc = r.conv("", T0, 128, 64, 64, 3, true, j, 2))) return rc;
   }
+  if ((rc = halo({bf.E}, 128))) return rc;
   // five multi-scale + CAC stages (:74-118)
   for (int s = 0; s < 5; ++s) {
     const size_t src = s == 0 ? bf.E : bf.F;
@@ -415,7 +446,8 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
       const bool tf[2] = {true, false};
       if ((rc = r.pair(src, 128, in_off, w3, w5, wp, tf, bf.MS, 128, out_off, out_add, 2))) return rc;
     }
-    const size_t pmap = (size_t)B * H * W * 8;     // bytes of one per-pixel float2 partial map
+    if ((rc = halo({bf.MS, bf.MS + half}, 128))) return rc;
+    const size_t pmap = bf.px * 8;                 // bytes of one per-pixel float2 partial map
     int pool_parts = 1;
     {
       Runner::FusedJob fj[2] = {{"conv3", "confuse", 0, bf.F, 128, 0, 0, 0, 0, false, bf.pooled, true},
@@ -430,6 +462,7 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
         j[1].in_add = half;
         if ((rc = r.conv("", bf.MS, 128, 128, 128, 5, true, j, 2))) return rc;
       }
+      if ((rc = halo({bf.R2, bf.R2 + half}, 128))) return rc;
       LayerJob j[2] = {{"confuse", 0, bf.F, 128, 0, 0, 0, 0, false}, {"confuse_c", 0, bf.F, 128, 64, 0, 0, 0, false}};
       j[1].in_add = half;
       if (tc_mode) {   // the 1x1 epilogues emit the per-branch ChannelPool partials (max, sum) per pixel
@@ -444,27 +477,49 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     float* part = reinterpret_cast<float*>(ws + bf.part);
     float* sc = reinterpret_cast<float*>(ws + bf.sc);
     // algorithmic HBM bytes: stats reads F (128e B/px); apply reads F and E, writes F (384e B/px)
-    {
-      ProfScope ps(ctx, PC_CAC_STATS, P * 128 * r.e, st);
-      if (tc_mode) CU_TRY(ctx, launch_cac_chan_stats(ws + bf.F, ctx->act, B, H, W, part, bf.chunks, st));
-      else CU_TRY(ctx, launch_cac_stats(ws + bf.F, ctx->act, B, H, W, pooled, part, bf.chunks, st));
-    }
-    {
+    if (!hook) {
+      {
+        ProfScope ps(ctx, PC_CAC_STATS, P * 128 * r.e, st);
+        if (tc_mode) CU_TRY(ctx, launch_cac_chan_stats(ws + bf.F, ctx->act, B, H, W, part, bf.chunks, st));
+        else CU_TRY(ctx, launch_cac_stats(ws + bf.F, ctx->act, B, H, W, pooled, part, bf.chunks, st));
+      }
       ProfScope ps(ctx, PC_CAC_MLP, 0.0, st);
       CU_TRY(ctx, launch_cac_mlp(part, bf.chunks, B, H * W, ctx->cac_w1[s], ctx->cac_b1[s], ctx->cac_w2[s],
                                  ctx->cac_b2[s], sc, st));
+    } else {
+      // band mode (B == 1): statistics over this band's core rows only, into its slot of the gathered buffer;
+      // the ChannelPool maps of the halo rows come from the neighbours; every GPU then reduces ALL bands'
+      // partials in the same fixed order, with the whole frame's pixel count
+      const int core_h = hook->cy1 - hook->cy0;
+      const size_t row0 = (size_t)hook->cy0 * W;
+      float* my_part = part + (size_t)hook->chunk_off * 256;
+      const int my_chunks = cac_stats_chunks(1, core_h, W);
+      if (tc_mode) {
+        CU_TRY(ctx, launch_cac_chan_stats(ws + bf.F + row0 * 128 * r.e, ctx->act, 1, core_h, W, my_part, my_chunks, st));
+        size_t o[4]; for (int k = 0; k < pool_parts; ++k) o[k] = bf.pooled + k * pmap;
+        size_t rb[4] = {(size_t)W * 8, (size_t)W * 8, (size_t)W * 8, (size_t)W * 8};
+        if ((rc = hook->halo(o, rb, pool_parts))) return rc;
+      } else {
+        CU_TRY(ctx, launch_cac_stats(ws + bf.F + row0 * 128 * r.e, ctx->act, 1, core_h, W, pooled + row0 * 2, my_part, my_chunks, st));
+        if ((rc = halo({bf.pooled}, 8, true))) return rc;
+      }
+      if ((rc = hook->gather_parts(bf.part))) return rc;
+      CU_TRY(ctx, launch_cac_mlp(part, hook->chunks_total, 1, (int)hook->global_hw, ctx->cac_w1[s], ctx->cac_b1[s],
+                                 ctx->cac_w2[s], ctx->cac_b2[s], sc, st));
     }
     {
       ProfScope ps(ctx, PC_CAC_APPLY, P * 384 * r.e, st);
-      CU_TRY(ctx, launch_cac_apply(ws + bf.F, ws + bf.E, ctx->act, pooled, sc, ctx->cac_ws[s], B, H, W, st, ctx->mode == CODON_MODE_TF32, pool_parts));
+      CU_TRY(ctx, launch_cac_apply(ws + bf.F, ws + bf.E, ctx->act, pooled, sc, ctx->cac_ws[s], B, H, W, st, ctx->mode == CODON_MODE_TF32, pool_parts, bf.px));
     }
     ctx->launches += 3;
+    if ((rc = halo({bf.F}, 128))) return rc;
   }
   // fusion head (:119-121): cat(out, out_c) is F itself
   {
     LayerJob j[1] = {{"conv7", 0, bf.FUSE, 64, 0, 0, 0, 0, false}};
     if ((rc = r.conv("", bf.F, 128, 128, 64, 3, true, j, 1))) return rc;
   }
+  if ((rc = halo({bf.FUSE}, 64))) return rc;
   // three fusion stages (:122-128)
   for (int k = 0; k < 3; ++k) {
     const size_t src = k == 0 ? bf.FUSE : bf.OF;
@@ -475,6 +530,7 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
       const bool tf[1] = {false};
       if ((rc = r.pair(src, 64, in_off, w3, w5, wp, tf, bf.MS, 128, out_off, out_add, 1))) return rc;
     }
+    if ((rc = halo({bf.MS}, 128))) return rc;
     {
       Runner::FusedJob fj[1] = {{"conv10", "confuse_fuse", 0, bf.OF, 64, 0, bf.FUSE, 64, 0, true, 0, false}};
       rc = r.conv5_fused(bf.MS, fj, 1);
@@ -485,21 +541,140 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
         LayerJob j[1] = {{"conv10", 0, bf.R2, 128, 0, 0, 0, 0, false}};
         if ((rc = r.conv("", bf.MS, 128, 128, 128, 5, true, j, 1))) return rc;
       }
+      if ((rc = halo({bf.R2}, 128))) return rc;
       LayerJob j[1] = {{"confuse_fuse", 0, bf.OF, 64, 0, bf.FUSE, 64, 0, true}};
       if ((rc = r.conv("", bf.R2, 128, 128, 64, 1, false, j, 1))) return rc;
     }
+    if ((rc = halo({bf.OF}, 64))) return rc;
   }
   // reconstruction (:129-131): conv11 into the MS region viewed as 64 ch, then output + x
   {
     LayerJob j[1] = {{"conv11", 0, bf.MS, 64, 0, 0, 0, 0, false}};
     if ((rc = r.conv("", bf.OF, 64, 64, 64, 3, true, j, 1))) return rc;
   }
+  if ((rc = halo({bf.MS}, 64))) return rc;
   {
     ProfScope ps(ctx, PC_EDGE, P * (8 + 64 * r.e), st);
     CU_TRY(ctx, launch_conv_last(ws + bf.MS, 64, ctx->act, ctx->w_out, x, out, B, H, W, st));
   }
   ctx->launches++;
   return CODON_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// codon_group: one frame over several GPUs of one process (row bands + NVLink peer-memory halo exchange)
+struct codon_group {
+  int n = 0;
+  std::vector<codon_ctx*> ctx;
+  std::vector<int> dev;
+  std::vector<cudaStream_t> st;
+  std::vector<uint8_t*> ws;          // per GPU workspace (identical layout on every GPU)
+  std::vector<float*> din, dout;     // per GPU band inputs (x | y) and output
+  std::vector<float*> pin;           // per GPU pinned staging (x | y | out)
+  size_t cap_px = 0, ws_cap = 0;     // capacity (pixels of the tallest band, workspace bytes)
+  std::vector<std::vector<cudaEvent_t>> ev;   // [gpu][layer]
+  // geometry of the current forward
+  int H = 0, W = 0;
+  std::vector<int> r0, r1, mt, mb, hloc, chunk_off, chunks;
+  int chunks_total = 0;
+  Buffers bf;
+  // host-side rendezvous of the per-GPU threads
+  std::atomic<int> arrived{0}, generation{0};
+  std::atomic<bool> failed{false};
+  std::mutex err_mu;
+  std::string err;
+  double last_ms = 0.0;
+
+  bool barrier() {   // sense-reversing spin barrier; gives up as soon as any thread has failed
+    const int gen = generation.load(std::memory_order_acquire);
+    if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+      arrived.store(0, std::memory_order_relaxed);
+      generation.fetch_add(1, std::memory_order_acq_rel);
+    } else {
+      while (generation.load(std::memory_order_acquire) == gen)
+        if (failed.load(std::memory_order_acquire)) return false;
+    }
+    return !failed.load(std::memory_order_acquire);
+  }
+  void set_error(const std::string& m) {
+    std::lock_guard<std::mutex> lk(err_mu);
+    if (err.empty()) err = m;
+    failed.store(true, std::memory_order_release);
+  }
+};
+
+namespace {
+
+constexpr int kGroupMaxLayers = 160;
+
+struct GroupHook : BandHook {
+  codon_group* G; int g; int layer = 0;
+  GroupHook(codon_group* G_, int g_) : G(G_), g(g_) {}
+
+  // records "my layer is done", meets the other threads, then makes my stream wait for the given peers
+  int rendezvous(bool all_peers) {
+    if (layer >= kGroupMaxLayers) { G->set_error("codon_group: too many layers"); return CODON_ERR_STATE; }
+    cudaStream_t st = G->st[g];
+    if (cudaEventRecord(G->ev[g][layer], st) != cudaSuccess) { G->set_error("cudaEventRecord failed"); }
+    if (!G->barrier()) return CODON_ERR_CUDA;
+    for (int h = 0; h < G->n; ++h) {
+      if (h == g || (!all_peers && h != g - 1 && h != g + 1)) continue;
+      if (cudaStreamWaitEvent(st, G->ev[h][layer], 0) != cudaSuccess) G->set_error("cudaStreamWaitEvent failed");
+    }
+    ++layer;
+    return G->failed.load() ? CODON_ERR_CUDA : CODON_OK;
+  }
+
+  int halo(const size_t* off, const size_t* rb, int nbuf) override {
+    int rc = rendezvous(false);
+    if (rc) return rc;
+    cudaStream_t st = G->st[g];
+    for (int i = 0; i < nbuf; ++i) {
+      const size_t bytes = (size_t)kBandHalo * rb[i];
+      if (g > 0) {          // my top halo rows <- the last core rows of the band above
+        const int h = g - 1;
+        const uint8_t* src = G->ws[h] + off[i] + (size_t)(G->hloc[h] - G->mb[h] - kBandHalo) * rb[i];
+        if (cudaMemcpyPeerAsync(G->ws[g] + off[i], G->dev[g], src, G->dev[h], bytes, st) != cudaSuccess)
+          G->set_error("cudaMemcpyPeerAsync failed");
+      }
+      if (g < G->n - 1) {   // my bottom halo rows <- the first core rows of the band below
+        const int h = g + 1;
+        const uint8_t* src = G->ws[h] + off[i] + (size_t)G->mt[h] * rb[i];
+        uint8_t* dst = G->ws[g] + off[i] + (size_t)(G->hloc[g] - G->mb[g]) * rb[i];
+        if (cudaMemcpyPeerAsync(dst, G->dev[g], src, G->dev[h], bytes, st) != cudaSuccess)
+          G->set_error("cudaMemcpyPeerAsync failed");
+      }
+    }
+    return G->failed.load() ? CODON_ERR_CUDA : CODON_OK;
+  }
+
+  int gather_parts(size_t part_off) override {
+    int rc = rendezvous(true);
+    if (rc) return rc;
+    cudaStream_t st = G->st[g];
+    for (int h = 0; h < G->n; ++h) {
+      if (h == g) continue;
+      const size_t o = part_off + (size_t)G->chunk_off[h] * 256 * sizeof(float);
+      const size_t bytes = (size_t)G->chunks[h] * 256 * sizeof(float);
+      if (cudaMemcpyPeerAsync(G->ws[g] + o, G->dev[g], G->ws[h] + o, G->dev[h], bytes, st) != cudaSuccess)
+        G->set_error("cudaMemcpyPeerAsync failed");
+    }
+    return G->failed.load() ? CODON_ERR_CUDA : CODON_OK;
+  }
+};
+
+void group_free_buffers(codon_group* G) {
+  for (int g = 0; g < G->n; ++g) {
+    cudaSetDevice(G->dev[g]);
+    if (G->ws[g]) cudaFree(G->ws[g]);
+    if (G->din[g]) cudaFree(G->din[g]);
+    if (G->dout[g]) cudaFree(G->dout[g]);
+    if (G->pin[g]) cudaFreeHost(G->pin[g]);
+    G->ws[g] = nullptr; G->din[g] = nullptr; G->dout[g] = nullptr; G->pin[g] = nullptr;
+  }
+  G->cap_px = 0; G->ws_cap = 0;
 }
 
 }  // namespace
@@ -923,6 +1098,128 @@ int codon_bicubic_upsample_f32(const float* src, float* dst, int B, int h, int w
   if (!src || !dst || B < 1 || h < 1 || w < 1 || H < 1 || W < 1)
     return fail(nullptr, CODON_ERR_ARG, "codon_bicubic_upsample_f32: bad argument");
   CU_TRY(nullptr, launch_bicubic_up(src, dst, B, h, w, H, W, static_cast<cudaStream_t>(cuda_stream)));
+  return CODON_OK;
+}
+
+int codon_group_create(codon_group** out, codon_ctx** ctxs, int n) {
+  if (!out || !ctxs || n < 1 || n > 16) return fail(nullptr, CODON_ERR_ARG, "codon_group_create: bad argument");
+  *out = nullptr;
+  for (int i = 0; i < n; ++i) {
+    if (!ctxs[i] || !ctxs[i]->finalized) return fail(nullptr, CODON_ERR_STATE, "codon_group_create: context %d has no finalized weights", i);
+    if (ctxs[i]->mode != ctxs[0]->mode || ctxs[i]->scale != ctxs[0]->scale) return fail(nullptr, CODON_ERR_ARG, "codon_group_create: contexts differ in mode / scale");
+    for (int j = 0; j < i; ++j)
+      if (ctxs[j]->device == ctxs[i]->device) return fail(nullptr, CODON_ERR_ARG, "codon_group_create: two contexts on device %d", ctxs[i]->device);
+  }
+  codon_group* G = new codon_group();
+  G->n = n;
+  G->ctx.assign(ctxs, ctxs + n);
+  G->dev.resize(n); G->st.resize(n); G->ws.assign(n, nullptr); G->din.assign(n, nullptr); G->dout.assign(n, nullptr);
+  G->pin.assign(n, nullptr); G->ev.resize(n);
+  G->r0.resize(n); G->r1.resize(n); G->mt.resize(n); G->mb.resize(n); G->hloc.resize(n); G->chunk_off.resize(n); G->chunks.resize(n);
+  for (int g = 0; g < n; ++g) G->dev[g] = ctxs[g]->device;
+  for (int g = 0; g < n; ++g) {
+    CU_TRY(nullptr, cudaSetDevice(G->dev[g]));
+    for (int h = 0; h < n; ++h) {
+      if (h == g) continue;
+      int can = 0;
+      CU_TRY(nullptr, cudaDeviceCanAccessPeer(&can, G->dev[g], G->dev[h]));
+      if (!can) { delete G; return fail(nullptr, CODON_ERR_CUDA, "codon_group_create: device %d cannot access device %d", G->dev[g], G->dev[h]); }
+      cudaError_t e = cudaDeviceEnablePeerAccess(G->dev[h], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { delete G; return fail(nullptr, CODON_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); }
+      cudaGetLastError();
+    }
+    CU_TRY(nullptr, cudaStreamCreateWithFlags(&G->st[g], cudaStreamNonBlocking));
+    G->ev[g].resize(kGroupMaxLayers);
+    for (auto& e : G->ev[g]) CU_TRY(nullptr, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  *out = G;
+  return CODON_OK;
+}
+
+void codon_group_destroy(codon_group* G) {
+  if (!G) return;
+  group_free_buffers(G);
+  for (int g = 0; g < G->n; ++g) {
+    cudaSetDevice(G->dev[g]);
+    for (auto& e : G->ev[g]) cudaEventDestroy(e);
+    if (G->st[g]) cudaStreamDestroy(G->st[g]);
+  }
+  delete G;
+}
+
+const char* codon_group_last_error(const codon_group* G) { return G ? G->err.c_str() : g_last_error.c_str(); }
+
+double codon_group_last_ms(const codon_group* G) { return G ? G->last_ms : 0.0; }
+
+int codon_group_forward_host(codon_group* G, const float* depth, const float* guide, float* out, int H, int W) {
+  if (!G || !depth || !guide || !out || H < 1 || W < 1) return fail(nullptr, CODON_ERR_ARG, "codon_group_forward_host: bad argument");
+  const int n = G->n;
+  if (H < n * 2 * kBandHalo) return fail(nullptr, CODON_ERR_ARG, "codon_group_forward_host: frame of %d rows is too small for %d bands", H, n);
+  // ---- band geometry: rows split evenly; interior sides carry kBandHalo halo rows ----------------
+  int hmax = 0;
+  G->H = H; G->W = W;
+  G->chunks_total = 0;
+  for (int g = 0; g < n; ++g) {
+    G->r0[g] = (int)((long)H * g / n); G->r1[g] = (int)((long)H * (g + 1) / n);
+    G->mt[g] = g > 0 ? kBandHalo : 0; G->mb[g] = g < n - 1 ? kBandHalo : 0;
+    G->hloc[g] = G->r1[g] - G->r0[g] + G->mt[g] + G->mb[g];
+    if (G->hloc[g] > hmax) hmax = G->hloc[g];
+    G->chunk_off[g] = G->chunks_total;
+    G->chunks[g] = cac_stats_chunks(1, G->r1[g] - G->r0[g], W);
+    G->chunks_total += G->chunks[g];
+  }
+  G->bf = plan_buffers(G->ctx[0], 1, hmax, W, G->chunks_total);
+  const size_t px = (size_t)hmax * W;
+  if (px > G->cap_px || G->bf.total > G->ws_cap) {
+    group_free_buffers(G);
+    for (int g = 0; g < n; ++g) {
+      CU_TRY(nullptr, cudaSetDevice(G->dev[g]));
+      void* p = nullptr;
+      CU_TRY(nullptr, cudaMalloc(&p, G->bf.total)); G->ws[g] = static_cast<uint8_t*>(p);
+      CU_TRY(nullptr, cudaMalloc(&p, 2 * px * sizeof(float))); G->din[g] = static_cast<float*>(p);
+      CU_TRY(nullptr, cudaMalloc(&p, px * sizeof(float))); G->dout[g] = static_cast<float*>(p);
+      CU_TRY(nullptr, cudaMallocHost(&p, 3 * px * sizeof(float))); G->pin[g] = static_cast<float*>(p);
+    }
+    G->cap_px = px; G->ws_cap = G->bf.total;
+  }
+  G->failed.store(false); G->arrived.store(0); G->err.clear();
+
+  auto worker = [&](int g) {
+    codon_ctx* ctx = G->ctx[g];
+    if (cudaSetDevice(G->dev[g]) != cudaSuccess) { G->set_error("cudaSetDevice failed"); return; }
+    cudaStream_t st = G->st[g];
+    const int y0 = G->r0[g] - G->mt[g], hl = G->hloc[g];
+    const size_t npx = (size_t)hl * W;
+    float* pin = G->pin[g];
+    memcpy(pin, depth + (size_t)y0 * W, npx * sizeof(float));
+    memcpy(pin + px, guide + (size_t)y0 * W, npx * sizeof(float));
+    bool ok = cudaMemcpyAsync(G->din[g], pin, npx * sizeof(float), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+              cudaMemcpyAsync(G->din[g] + px, pin + px, npx * sizeof(float), cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (!ok) { G->set_error("band upload failed"); return; }
+    GroupHook hook(G, g);
+    hook.cy0 = G->mt[g]; hook.cy1 = hl - G->mb[g];
+    hook.global_hw = (long)H * W;
+    hook.chunk_off = G->chunk_off[g]; hook.chunks_total = G->chunks_total;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(G->ws[g]), 1024));
+    ctx->launches = 0;
+    int rc = run_forward(ctx, G->din[g], G->din[g] + px, G->dout[g], 1, hl, W, ws, G->bf, st, &hook);
+    if (rc) { G->set_error(std::string("band ") + std::to_string(g) + ": " + ctx->err); return; }
+    const size_t core_px = (size_t)(G->r1[g] - G->r0[g]) * W;
+    if (cudaMemcpyAsync(pin + 2 * px, G->dout[g] + (size_t)G->mt[g] * W, core_px * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { G->set_error(std::string("band ") + std::to_string(g) + ": " + cudaGetErrorString(cudaGetLastError())); return; }
+    memcpy(out + (size_t)G->r0[g] * W, pin + 2 * px, core_px * sizeof(float));
+  };
+  // the aligned workspace base must be the same offset on every GPU (cudaMalloc returns >= 256-B aligned
+  // pointers; the layout offsets are relative to the 1024-aligned base, and peers address ws[h] + offset)
+  for (int g = 0; g < n; ++g)
+    if (reinterpret_cast<uintptr_t>(G->ws[g]) % 1024 != 0) return fail(nullptr, CODON_ERR_CUDA, "codon_group: workspace not 1024-byte aligned");
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int g = 1; g < n; ++g) th.emplace_back(worker, g);
+  worker(0);
+  for (auto& t : th) t.join();
+  G->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (G->failed.load()) return fail(nullptr, CODON_ERR_CUDA, "codon_group_forward_host: %s", G->err.c_str());
   return CODON_OK;
 }
 

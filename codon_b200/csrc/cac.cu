@@ -349,9 +349,10 @@ cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const f
 }
 
 cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* pooled, const float* sc,
-                             const float* ws, int B, int H, int W, cudaStream_t st, int rnd_tf32, int pool_parts) {
+                             const float* ws, int B, int H, int W, cudaStream_t st, int rnd_tf32, int pool_parts,
+                             size_t part_stride) {
   const int tiles_x = cdiv(W, kATW);
-  const size_t part_stride = (size_t)B * H * W;
+  if (part_stride == 0) part_stride = (size_t)B * H * W;
   dim3 grid(tiles_x * cdiv(H, kATH), B);
   if (act == ACT_F32) cac_apply_kernel<float><<<grid, 256, 0, st>>>((float*)F, (const float*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride);
   else if (act == ACT_BF16) cac_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)F, (const __nv_bfloat16*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride);

@@ -65,6 +65,7 @@ struct TcKParams {
   int npb;                       // patch stages in the ring (2 .. kMaxNPB)
   uint32_t idesc_1x1;            // fused 1x1: kind::f16, M = 256, N = 64
   int fuse_njobs;
+  unsigned long long pool_stride;   // fused mode: pixels between the two half-channel pool maps of a job
   int debug;   // CODON_TC_DEBUG bits (perf experiments only, 1-CTA kernel): 1 no epilogue stores, 2 no B loads, 4 no A loads, 8 no MMAs, 16 no waits
 };
 
@@ -839,7 +840,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
               float mxv = __uint_as_float(r[0]), sacc = 0.f;
 #pragma unroll
               for (int e = 0; e < 32; ++e) { const float v = __uint_as_float(r[e]); mxv = fmaxf(mxv, v); sacc += v; }
-              job.pool[(size_t)ehalf * ((size_t)p.B * p.H * p.W) + pix] = make_float2(mxv, sacc);
+              job.pool[(size_t)ehalf * (size_t)p.pool_stride + pix] = make_float2(mxv, sacc);
             }
           }
         };
@@ -1198,6 +1199,7 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, c
         return cudaErrorInvalidValue;
       kp.idesc_1x1 = make_idesc(L.y16_operand, 64, 256);
       kp.fuse_njobs = L.njobs;
+      kp.pool_stride = L.pool_stride ? L.pool_stride : (unsigned long long)L.B * L.H * L.W;
       const CUtensorMap& w0 = *L.wmap[0];
       const CUtensorMap& w1 = *L.wmap[L.njobs > 1 ? 1 : 0];
 #define CODON_TC2F_DISPATCH(N)                                                          \

@@ -51,7 +51,8 @@ cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const f
 // ws fp32 [2][25] (max map taps, then mean map taps).
 cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* pooled, const float* sc,
                              const float* ws, int B, int H, int W, cudaStream_t st, int rnd_tf32 = 0,
-                             int pool_parts = 1);   // 1: pooled = final (max, mean) [B,H,W,2]; 2: two (max, sum) partial maps
+                             int pool_parts = 1,    // 1: pooled = final (max, mean) [B,H,W,2]; 2 / 4: (max, sum) partial maps
+                             size_t part_stride = 0);   // pixels between the partial maps (0: B*H*W)
 
 // ---- utility -------------------------------------------------------------------------------------
 cudaError_t launch_convert_to_f32(const void* src, int dtype, float* dst, size_t n, cudaStream_t st);

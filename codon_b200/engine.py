@@ -28,6 +28,8 @@ ABI_SYMBOLS = [
     "codon_cac_apply", "codon_channel_stats", "codon_channel_pool", "codon_conv2d_nchw",
     "codon_masked_rmse", "codon_ssim_gauss", "codon_quantise_u8",
     "codon_bgr_to_gray_u8", "codon_u8_to_unit_f32", "codon_bicubic_upsample_f32",
+    "codon_group_create", "codon_group_destroy", "codon_group_forward_host", "codon_group_last_error",
+    "codon_group_last_ms",
 ]
 
 _lib = None
@@ -84,10 +86,19 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         lib.codon_bgr_to_gray_u8.argtypes = [vp, vp, c.c_size_t, ip, vp]
         lib.codon_u8_to_unit_f32.argtypes = [vp, vp, c.c_size_t, vp]
         lib.codon_bicubic_upsample_f32.argtypes = [vp, vp, ip, ip, ip, ip, ip, vp]
+        lib.codon_group_create.argtypes = [c.POINTER(vp), c.POINTER(vp), ip]
+        lib.codon_group_destroy.argtypes = [vp]
+        lib.codon_group_destroy.restype = None
+        lib.codon_group_forward_host.argtypes = [vp, vp, vp, vp, ip, ip]
+        lib.codon_group_last_error.argtypes = [vp]
+        lib.codon_group_last_error.restype = c.c_char_p
+        lib.codon_group_last_ms.argtypes = [vp]
+        lib.codon_group_last_ms.restype = c.c_double
         for name in ABI_SYMBOLS:
             fn = getattr(lib, name)
             if name not in ("codon_destroy", "codon_last_error", "codon_version", "codon_workspace_bytes",
-                            "codon_profile_category_name"):
+                            "codon_profile_category_name", "codon_group_destroy", "codon_group_last_error",
+                            "codon_group_last_ms"):
                 fn.restype = c.c_int
         if path is None:
             _lib = lib
@@ -476,3 +487,50 @@ def bicubic_upsample(lr: torch.Tensor, H: int, W: int) -> torch.Tensor:
     with torch.cuda.device(src.device):
         check(lib.codon_bicubic_upsample_f32(src.data_ptr(), dst.data_ptr(), B, h, w, H, W, current_stream_ptr(src.device)))
     return dst.reshape(*shp[:-2], H, W)
+
+
+# ---- one frame over several GPUs -----------------------------------------------------------------------
+
+class FrameGroup:
+    """Single-frame latency mode: one frame is split into horizontal bands, one per GPU of
+    this process; halo rows travel over NVLink peer memory after every layer and the CAC channel
+    statistics are all-gathered (codon_group_* in include/codon_b200.h).  No NCCL, no torch.distributed."""
+
+    def __init__(self, scale: int, mode: str, devices, state_dict: Dict[str, torch.Tensor]):
+        self.lib = load_library()
+        self.engines = [Engine(scale, mode, int(d)) for d in devices]
+        for e in self.engines:
+            e.load_state_dict(state_dict)
+        arr = (ctypes.c_void_p * len(self.engines))(*[e._ctx for e in self.engines])
+        self._grp = ctypes.c_void_p()
+        check(self.lib.codon_group_create(ctypes.byref(self._grp), arr, len(self.engines)))
+
+    def forward_host(self, depth, guide):
+        """HOST float32 [H,W] arrays in, [H,W] out (copies and the cross-GPU exchange included)."""
+        import numpy as np
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        g = np.ascontiguousarray(guide, dtype=np.float32)
+        if d.ndim != 2 or d.shape != g.shape:
+            raise CodonError("FrameGroup.forward_host needs two [H,W] arrays of one shape")
+        out = np.empty_like(d)
+        rc = self.lib.codon_group_forward_host(self._grp, d.ctypes.data, g.ctypes.data, out.ctypes.data, d.shape[0], d.shape[1])
+        if rc != 0:
+            raise CodonError(f"libcodon_b200 error {rc}: {self.lib.codon_group_last_error(None).decode()}")
+        return out
+
+    @property
+    def last_ms(self) -> float:
+        return float(self.lib.codon_group_last_ms(self._grp))
+
+    def close(self):
+        if getattr(self, "_grp", None) and self._grp.value:
+            self.lib.codon_group_destroy(self._grp)
+            self._grp = ctypes.c_void_p()
+        for e in getattr(self, "engines", []):
+            e.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -173,6 +173,20 @@ int codon_ssim_gauss(const void* img1, const void* img2, int img_dtype, int B, i
                      double c1, double c2, double* ssim, void* workspace, size_t workspace_bytes,
                      void* cuda_stream);
 
+/* ---- one frame over several GPUs (SURVEY.md 8e "single-frame latency mode") ----------------------
+ * A group owns one finalized context per GPU (same scale / mode / weights, distinct devices with peer
+ * access).  codon_group_forward_host splits ONE H x W frame into horizontal bands, one per GPU; after every
+ * layer each GPU pulls 2 halo rows from its neighbours' bands over NVLink peer memory, and the per-band CAC
+ * channel statistics are all-gathered so that every GPU evaluates the same gates.  No NCCL.  depth / guide /
+ * out are HOST fp32 [H, W].  The result equals the single-GPU forward up to the summation order of the CAC
+ * average pool. */
+typedef struct codon_group codon_group;
+int codon_group_create(codon_group** out, codon_ctx** ctxs, int n);
+void codon_group_destroy(codon_group* group);
+int codon_group_forward_host(codon_group* group, const float* depth, const float* guide, float* out, int H, int W);
+const char* codon_group_last_error(const codon_group* group);
+double codon_group_last_ms(const codon_group* group);   /* wall-clock milliseconds of the last forward_host */
+
 /* ---- driver pre-processing on the GPU (DEVICE pointers) ------------------------------------------
  * Replaces the colour -> gray conversion of cv2.imread(path, 0) (CODON_X4/test.py:118) for an already decoded
  * 8-bit BGR image [n_pixels, 3].  method 0: what imread(.., 0) yields for a colour PNG (libpng's

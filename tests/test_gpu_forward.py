@@ -224,3 +224,26 @@ def test_two_gpus_one_process_same_bits():
     outs = sch.MultiGpuExecutor([0, 1]).map(run, list(range(4)))
     for i, o in enumerate(outs):
         assert torch.equal(o, ref[i:i + 1])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+def test_single_frame_over_gpus_matches_single_gpu(mode):
+    """codon_group_*: one frame split into row bands over the GPUs (NVLink peer halo exchange after every layer,
+    all-gathered CAC statistics).  Equals the single-GPU forward up to the summation order of the average pool."""
+    n = min(torch.cuda.device_count(), 4)
+    sd = orc.synthetic_state_dict(4, 0)
+    for (h, w) in ((203, 176), (480, 640)):
+        x, y = orc.synthetic_frames(1, h, w, 17)
+        net = _net(4, 0, mode)
+        with torch.no_grad():
+            ref = net(x.cuda(0), y.cuda(0)).cpu().numpy()[0, 0]
+        grp = engine.FrameGroup(4, mode, list(range(n)), sd)
+        got = grp.forward_host(x.numpy()[0, 0], y.numpy()[0, 0])
+        again = grp.forward_host(x.numpy()[0, 0], y.numpy()[0, 0])
+        grp.close()
+        err = float(np.abs(got - ref).max())
+        print(f"{mode} {h}x{w} over {n} GPUs: max |band - single| = {err:.3e}")
+        assert np.array_equal(got, again)
+        # the gate differs by ~1e-7 (summation order); 16-bit / tf32 rounding then amplifies that to the mode's own rounding noise
+        assert err <= (2e-6 if mode == "fp32" else 5e-4 if mode != "bf16" else 4e-3)
