@@ -31,6 +31,8 @@
 #include <cstdlib>
 #include <cmath>
 #include <atomic>
+#include <utility>
+#include <type_traits>
 #include "common.cuh"
 #include "kernels.h"
 #include "conv_tc.h"
@@ -44,9 +46,19 @@ constexpr int kMaxNPB = 8;                     // patch stages: as many as fit (
 constexpr int kBStages = 4;
 constexpr uint32_t kBStageBytes = 128 * 128;   // up to 128 rows x 128 B
 constexpr int kThreads = 320;                  // warp 0 producer, 1 MMA, 2-9 epilogue (two warps per TMEM lane quarter)
-constexpr int kThreads2 = 352;                 // warp 0 A producer, 1 MMA, 2-9 epilogue, 10 B producer
-constexpr int kB2Stages = 8;
-constexpr uint32_t kB2StageBytes = 64 * 128;   // half of an (at most) 128-row block
+// Cluster kernel: warps 0-7 epilogue (two per TMEM lane quarter), 8 A producer, 9 MMA issuer (+ TMEM owner), 10 B producer.
+// The single-thread roles are the HIGHEST warp ids of their scheduler partition (warp % 4): the arbiter favours the
+// highest warp id, so the latency-critical issue loop never queues behind the epilogue's ALU work.
+constexpr int kThreads2 = 352;
+constexpr int kWarpA = 8, kWarpMma = 9, kWarpB = 10;
+constexpr int kB2MaxStages = 9;                // barrier slots reserved for the weight ring of the cluster kernel
+// Perf-experiment knobs of the cluster kernel (CODON_TC_DEBUG bits, cycle accounting) exist only in builds with
+// -DCODON_TC_EXPERIMENT: the MMA issue loop is latency-bound, every extra instruction in it costs throughput.
+#ifdef CODON_TC_EXPERIMENT
+#define TC2_DBG(p, bit) (((p).debug & (bit)) != 0)
+#else
+#define TC2_DBG(p, bit) false
+#endif
 constexpr uint32_t kBarBytes = 1024;           // barrier block at the start of the dynamic smem
 
 struct TcKParams {
@@ -66,13 +78,48 @@ struct TcKParams {
   uint32_t idesc_1x1;            // fused 1x1: kind::f16, M = 256, N = 64
   int fuse_njobs;
   unsigned long long pool_stride;   // fused mode: pixels between the two half-channel pool maps of a job
-  int debug;   // CODON_TC_DEBUG bits (perf experiments only, 1-CTA kernel): 1 no epilogue stores, 2 no B loads, 4 no A loads, 8 no MMAs, 16 no waits
+  int debug;   // CODON_TC_DEBUG bits (perf experiments only; results are garbage): 1 no epilogue stores, 2 no B loads, 4 no A loads,
+               // 8 no MMAs (1-CTA), 16 no waits (1-CTA), 32 no epilogue TMEM loads / Y staging (cluster kernel)
 };
 
 template <int NACC> struct Geo {
   static constexpr int NAX = NACC >= 2 ? 2 : 1, NAY = NACC / NAX;
   static constexpr int TW = NAX * kTcSubW, TH = NAY * kTcSubH;
 };
+
+// Tap schedule of the cluster kernel, known at compile time so that the MMA issuer and the weight producer are
+// straight-line code per tap (descriptor offsets and byte counts are immediates).  Must match fill_orders() /
+// tc_make_plan() / tc_make_pair_plan() below (checked on the host before every launch).
+enum TcKind : int { TK_3X3 = 0, TK_5X5 = 1, TK_PAIR = 2 };
+template <int KIND> struct Taps {
+  static constexpr int KS = KIND == TK_3X3 ? 3 : 5;
+  static constexpr int NT = KS * KS;
+  // weight ring of the cluster kernel: stage count (divides NT) and bytes per stage = this CTA's half of the largest
+  // block of the kind (3x3: 64 rows -> 32 x 128 B; 5x5 / pair: 128 rows -> 64 x 128 B)
+  static constexpr int NST = KIND == TK_3X3 ? 9 : 5;
+  static constexpr uint32_t kStageBytes = KIND == TK_3X3 ? 4096u : 8192u;
+  __host__ __device__ static constexpr int ord(int i) {
+    return KIND == TK_PAIR ? (i == 0 ? 2 : i == 1 ? 1 : i == 2 ? 3 : i == 3 ? 0 : 4) : i;
+  }
+  __host__ __device__ static constexpr int dx(int t) { return ord(t / KS); }     // issue order: dx outer, dy inner
+  __host__ __device__ static constexpr int dy(int t) { return ord(t % KS); }
+  // pair plans: the 16 border taps belong to the 5x5 convolution only (64 weight rows, N = 64)
+  __host__ __device__ static constexpr bool outer(int t) {
+    return KIND == TK_PAIR && (dx(t) == 0 || dx(t) == 4 || dy(t) == 0 || dy(t) == 4);
+  }
+  // pair plans: 64-row (8 KB) units of one slab's weight stream that precede tap t
+  __host__ __device__ static constexpr int units_before(int t) {
+    int u = 0;
+    for (int i = 0; i < t; ++i) u += outer(i) ? 1 : 2;
+    return u;
+  }
+};
+template <typename F, int... Is>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, Is...>) {
+  (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -88,26 +135,29 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  long long t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    // watchdog: a protocol bug must fault, never hang the GPU
-    const long long now = clock64();
-    if (t0 == 0) t0 = now;
-    else if (now - t0 > 4000000000LL) {
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// slow path of a wait, out of line: spins with a watchdog (a protocol bug must fault, never hang the GPU)
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
       printf("conv_tc: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
                                             int c2, int c3) {
@@ -525,12 +575,14 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, u
 __device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// non-blocking phase test with cluster-scope acquire (the arrivals come from both CTAs of the pair)
-__device__ __forceinline__ bool mbar_test_cluster(uint32_t bar, uint32_t parity) {
+// Non-blocking phase test.  CTA-scope acquire, also for barriers the peer CTA arrives on with a cluster-scope
+// release: a cluster-scope acquire here costs a few thousand cycles per call (CCTL.IVALL + fence, measured with
+// CODON_TC_DEBUG=64), and what the waiter goes on to touch is TMEM / the async proxy, not generic-proxy data.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   return done != 0;
@@ -584,7 +636,7 @@ __device__ __forceinline__ Tile2 decode_tile2(const TcKParams& p, int item, int 
 // the resident 1x1 weights (8 MMAs, N = 64) into the first 64 columns of the same accumulator, and the
 // epilogue drains those (+ the fusion-stage residual) to global memory.  The 128-channel intermediate never
 // touches HBM and the stand-alone 1x1 launch disappears.
-template <int NACC, int OPERAND, bool FUSE>
+template <int NACC, int OPERAND, bool FUSE, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
                 const __grid_constant__ CUtensorMap bmap0, const __grid_constant__ CUtensorMap bmap1,
@@ -592,7 +644,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
                 const __grid_constant__ TcKParams p) {
   using OutT = typename OperandTraits<OPERAND>::Out;
   using G = Geo<NACC>;
+  using TP = Taps<KIND>;
+  // Weight ring: NST stages whose count divides the taps of a slab, so that the stage of tap t (t % NST) and the
+  // use count inside a slab (t / NST) are compile-time constants; the only run-time state is one parity bit per slab.
+  constexpr int NST = TP::NST;
+  constexpr uint32_t kStageBytes = TP::kStageBytes;
+  static_assert(TP::NT % NST == 0 && NST <= kB2MaxStages, "ring must divide the tap count");
+  constexpr int kUsesPerSlab = TP::NT / NST;     // odd (1 or 5): the parity of a stage flips from slab to slab
   constexpr int Y16 = OPERAND == TC_BF16 ? TC_BF16 : TC_F16;   // tf32 mode stages Y in fp16 (same 10-bit mantissa)
+  constexpr uint32_t kPitch = (uint32_t)(G::TW + TP::KS - 1) * 128u;   // patch row pitch in bytes (== p.pw * 128)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -600,14 +660,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   const uint32_t s_patch = sbase + kBarBytes;
   const uint32_t s_b = s_patch + p.npb * p.patch_stage;
   const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * kMaxNPB;
-  const uint32_t bar_b_full = s_bar + 16 * kMaxNPB, bar_b_empty = bar_b_full + 8 * kB2Stages;
-  const uint32_t bar_acc_full = bar_b_empty + 8 * kB2Stages, bar_acc_empty = bar_acc_full + 16;
+  const uint32_t bar_b_full = s_bar + 16 * kMaxNPB, bar_b_empty = bar_b_full + 8 * kB2MaxStages;
+  const uint32_t bar_acc_full = bar_b_empty + 8 * kB2MaxStages, bar_acc_empty = bar_acc_full + 16;
   const uint32_t bar_y_full = bar_acc_empty + 16, bar_y_done = bar_y_full + 8, bar_wc_full = bar_y_done + 8;
   const uint32_t s_tmem_slot = bar_wc_full + 8;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (s_tmem_slot - smem_u32(smem_raw)));
   // fused mode: [1x1 weights: 2 jobs x 2 slabs x 32 rows x 128 B = 16 KB][Y: 2 slabs x 128 rows x 128 B = 32 KB]
-  const uint32_t s_wc = s_b + kB2Stages * kB2StageBytes;
+  const uint32_t s_wc = s_b + NST * kStageBytes;
   const uint32_t s_y = s_wc + 16384;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -615,20 +675,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   const int total_items = p.total_items;
-  const uint32_t pitch = (uint32_t)p.pw * 128u;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpA && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap1) : "memory");
     for (int i = 0; i < p.npb; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
-    for (int i = 0; i < kB2Stages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 512); }
     mbar_init(bar_y_full, 512); mbar_init(bar_y_done, 1); mbar_init(bar_wc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem_slot), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -639,7 +698,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0) {
+  if (warp == kWarpA) {
     // ================================ A producer (both CTAs): one activation patch per slab ======
     int ps = 0;
     uint32_t pph = 0;
@@ -650,18 +709,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
       for (int s = 0; s < p.nslab; ++s) {
         mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
         if (elect_one()) {
-          if (leader) mbar_expect_tx(bar_patch_full + 8 * ps, 2 * p.patch_tx);
-          tma_load_4d_2sm(s_patch + ps * p.patch_stage, tl.job ? &tmap1 : &tmap0, full_leader + 8 * ps,
-                          coff + s * p.slab_elems, tl.x0 - p.pad, tl.y0 - p.pad, tl.n);
+          if (TC2_DBG(p, 4)) { if (leader) mbar_arrive(bar_patch_full + 8 * ps); }
+          else {
+            if (leader) mbar_expect_tx(bar_patch_full + 8 * ps, 2 * p.patch_tx);
+            tma_load_4d_2sm(s_patch + ps * p.patch_stage, tl.job ? &tmap1 : &tmap0, full_leader + 8 * ps,
+                            coff + s * p.slab_elems, tl.x0 - p.pad, tl.y0 - p.pad, tl.n);
+          }
         }
         __syncwarp();
         if (++ps == p.npb) { ps = 0; pph ^= 1; }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == kWarpB) {
     // ================================ B producer (both CTAs): this CTA's half of every weight block
-    int bs = 0;
-    uint32_t bph = 0;
+    uint32_t slab_par = 0;                       // parity of the ring uses of the current slab (flips per slab)
     const uint32_t full_leader = mapa_u32(bar_b_full, 0);
     if (FUSE && elect_one()) {
       // resident 1x1 weights: this CTA's 32 of the 64 output rows, per job and 128-byte K slab
@@ -673,34 +734,43 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
                           (int)((sl * 8192u + rank * 4096u) >> 7));
     }
     __syncwarp();
+    // rows (128 B) of one tap's weight block: the pair plan mixes 128-row (inner) and 64-row (outer) blocks
+    const int tap_rows = p.n_cols;
     for (int item = cluster_id; item < total_items; item += nclusters) {
       const Tile2 tl = decode_tile2<NACC>(p, item, (int)rank);
       const CUtensorMap* bm = tl.job ? &bmap1 : &bmap0;
       for (int s = 0; s < p.nslab; ++s) {
-        for (int dxi = 0; dxi < p.ndx; ++dxi) {
-          for (int dyi = 0; dyi < p.ndy; ++dyi) {
-            mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
-            if (elect_one()) {
-              const uint32_t bytes = p.b_bytes[dxi][dyi], half = bytes >> 1;
-              if (leader) mbar_expect_tx(bar_b_full + 8 * bs, bytes);
-              const int row0 = (int)(((uint32_t)s * p.slab_bytes + p.b_off[dxi][dyi] + rank * half) >> 7);
-              const uint32_t dst = s_b + bs * kB2StageBytes;
-              tma_load_2d_2sm(dst, bm, full_leader + 8 * bs, 0, row0);
-              if (half > 4096) tma_load_2d_2sm(dst + 4096, bm, full_leader + 8 * bs, 0, row0 + 32);
+        const int slab_row0 = (int)(((uint32_t)s * p.slab_bytes) >> 7);
+        static_for<TP::NT>([&](auto T) {
+          constexpr int t = decltype(T)::value;
+          constexpr bool outer = TP::outer(t);
+          constexpr int st = t % NST;
+          mbar_wait(bar_b_empty + 8 * st, slab_par ^ (uint32_t)((t / NST) & 1) ^ 1u);
+          if (elect_one()) {
+            // this CTA's half of the block: rows [rank * rows/2, (rank + 1) * rows/2) in 32-row (4 KB) boxes
+            const int rows = KIND == TK_PAIR ? (outer ? 64 : 128) : tap_rows;
+            const int row0 = slab_row0 + (KIND == TK_PAIR ? TP::units_before(t) * 64 : t * tap_rows) + (int)rank * (rows >> 1);
+            if (TC2_DBG(p, 2)) { if (leader) mbar_arrive(bar_b_full + 8 * st); }
+            else {
+              if (leader) mbar_expect_tx(bar_b_full + 8 * st, (uint32_t)rows << 7);
+              const uint32_t dst = s_b + (uint32_t)st * kStageBytes;
+              tma_load_2d_2sm(dst, bm, full_leader + 8 * st, 0, row0);
+              if (rows > 64) tma_load_2d_2sm(dst + 4096, bm, full_leader + 8 * st, 0, row0 + 32);
             }
-            __syncwarp();
-            if (++bs == kB2Stages) { bs = 0; bph ^= 1; }
           }
-        }
+          __syncwarp();
+        });
+        slab_par ^= (uint32_t)(kUsesPerSlab & 1);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // ================================ MMA issuer (leader CTA only) ===============================
     if (leader) {
-      int ps = 0, bs = 0;
-      uint32_t pph = 0, bph = 0;
+      int ps = 0;
+      uint32_t pph = 0, slab_par = 0;
       int it = 0;
-      const uint64_t desc_a = umma_desc_hi(pitch), desc_b = umma_desc_hi(1024);
+      const uint64_t desc_a = umma_desc_hi(kPitch), desc_b = umma_desc_hi(1024);
+      const uint64_t b_base = desc_b | desc_addr(s_b);
       // fused 1x1: uses (accumulators) of the previous tile that are still to be multiplied
       int prev_left = 0, prev_j = 0, prev_job = 0;
       uint32_t prev_d = 0, y_uses = 0;
@@ -708,8 +778,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
       auto service = [&](bool block) {
         // issues the 1x1 MMAs of the next pending accumulator once its Y tile is complete in both CTAs
         while (prev_left > 0) {
-          if (block) { while (!mbar_test_cluster(bar_y_full, y_uses & 1u)) {} }
-          else if (!mbar_test_cluster(bar_y_full, y_uses & 1u)) return;
+          if (block) mbar_wait(bar_y_full, y_uses & 1u);
+          else if (!mbar_test(bar_y_full, y_uses & 1u)) return;
           if (!wc_ready) { mbar_wait(bar_wc_full, 0); wc_ready = true; }
           tc_fence_after();
           if (elect_one()) {
@@ -726,55 +796,83 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           ++y_uses; ++prev_j; --prev_left;
         }
       };
+      const uint32_t idesc_full = p.idesc_full, idesc_half = p.idesc_half;
+      const uint32_t n_cols = (uint32_t)p.n_cols;
+#ifdef CODON_TC_EXPERIMENT
+      // CODON_TC_DEBUG bit 64: cycle accounting of this warp (cluster 0 prints it when the kernel ends)
+      const bool prof = (p.debug & 64) != 0;
+      long long c_wait = 0, c_all = prof ? clock64() : 0, c_t = 0;
+      int n_taps = 0;
+#endif
       for (int item = cluster_id; item < total_items; item += nclusters, ++it) {
         const Tile2 tl = decode_tile2<NACC>(p, item, 0);
-        const int outer_col = p.job[tl.job].outer_col;
+        const uint32_t outer_col = (uint32_t)p.job[tl.job].outer_col;
         const int buf = it % p.nbuf;
         const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
         if (FUSE) {
           // the epilogue of the tile that last used this TMEM buffer needs our 1x1 MMAs to finish: keep serving
-          while (!mbar_test_cluster(bar_acc_empty + 8 * buf, aph ^ 1)) service(false);
+          while (!mbar_test(bar_acc_empty + 8 * buf, aph ^ 1)) service(false);
         } else {
           mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
         }
         tc_fence_after();
-        const uint32_t d_base = tmem_base + (uint32_t)(buf * NACC * p.n_cols);
-        uint32_t acc0 = 0;
+        const uint32_t d_base = tmem_base + (uint32_t)buf * (uint32_t)NACC * n_cols;
+        const int nacc_rt = tl.nacc;
+        uint32_t acc0 = 0;                         // 0 only for the first K step of the tile
         for (int s = 0; s < p.nslab; ++s) {
           mbar_wait(bar_patch_full + 8 * ps, pph);
-          const uint32_t patch = s_patch + ps * p.patch_stage;
-          for (int dxi = 0; dxi < p.ndx; ++dxi) {
-            for (int dyi = 0; dyi < p.ndy; ++dyi) {
-              if (FUSE) service(false);
-              mbar_wait(bar_b_full + 8 * bs, bph);
-              tc_fence_after();
-              const bool half = p.b_bytes[dxi][dyi] < (uint32_t)p.n_cols * 128u;
-              const uint32_t idesc = half ? p.idesc_half : p.idesc_full;
-              const uint32_t d0 = d_base + (half ? (uint32_t)outer_col : 0u);
-              const uint64_t bdesc = desc_b | desc_addr(s_b + bs * kB2StageBytes);
-              const uint64_t adesc0 = desc_a | desc_addr(patch + (uint32_t)p.dy_ord[dyi] * pitch + (uint32_t)p.dx_ord[dxi] * 128u);
-              const bool last = (dxi == p.ndx - 1) && (dyi == p.ndy - 1);
-              if (elect_one()) {
+          const uint64_t a_base = desc_a | desc_addr(s_patch + ps * p.patch_stage);
+          const bool last_slab = s == p.nslab - 1;
+          const uint32_t par_even = slab_par, par_odd = slab_par ^ 1u;
+          // Straight-line code per tap: the A start address is the patch shifted by (dy rows, dx pixels), the ring
+          // stage and its barriers are immediates.  The phase test of the NEXT tap's weights is issued before this
+          // tap's MMAs so that its latency hides behind their issue.
+          bool ready = mbar_test(bar_b_full, par_even);
+          static_for<TP::NT>([&](auto T) {
+            constexpr int t = decltype(T)::value;
+            constexpr bool outer = TP::outer(t);
+            constexpr int st = t % NST;
+            constexpr uint32_t tap_off = ((uint32_t)TP::dy(t) * kPitch + (uint32_t)TP::dx(t) * 128u) >> 4;
+            if (FUSE) service(false);
+#ifdef CODON_TC_EXPERIMENT
+            if (prof) c_t = clock64();
+#endif
+            if (!ready) mbar_wait(bar_b_full + 8 * st, ((t / NST) & 1) ? par_odd : par_even);
+#ifdef CODON_TC_EXPERIMENT
+            if (prof) { c_wait += clock64() - c_t; ++n_taps; }
+#endif
+            if (t + 1 < TP::NT) ready = mbar_test(bar_b_full + 8 * ((t + 1) % NST), (((t + 1) / NST) & 1) ? par_odd : par_even);
+            tc_fence_after();
+            const uint64_t bdesc = b_base + (uint64_t)(((uint32_t)st * kStageBytes) >> 4);
+            const uint32_t idesc = outer ? idesc_half : idesc_full;
+            const uint32_t d0 = d_base + (outer ? outer_col : 0u);
+            if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < NACC; ++j) {
-                  if (j >= tl.nacc) break;
-                  const uint64_t adesc = adesc0 + (uint64_t)(((j / G::NAX) * kTcSubH * pitch + (j % G::NAX) * kTcSubW * 128u) >> 4);
-                  const uint32_t d = d0 + (uint32_t)(j * p.n_cols);
+              for (int j = 0; j < NACC; ++j) {
+                if (j < nacc_rt && !TC2_DBG(p, 8)) {
+                  // sub-tile j = (jx, jy): + jy*16 patch rows + jx*8 pixels
+                  const uint32_t sub_off = ((uint32_t)(j / G::NAX) * kTcSubH * kPitch + (uint32_t)(j % G::NAX) * kTcSubW * 128u) >> 4;
+                  const uint64_t adesc = a_base + (uint64_t)(tap_off + sub_off);
+                  const uint32_t d = d0 + (uint32_t)j * n_cols;
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    if (OPERAND == TC_TF32) umma_tf32_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? acc0 : 1u);
-                    else                    umma_f16_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? acc0 : 1u);
+                    // +32 B per K step inside the 128-B swizzled row == +2 in the 16-B address field
+                    const uint32_t acc = (t == 0 && k == 0) ? acc0 : 1u;
+                    if (OPERAND == TC_TF32) umma_tf32_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                    else                    umma_f16_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
                   }
                 }
-                umma_commit_2sm(bar_b_empty + 8 * bs);
-                if (last) umma_commit_2sm(bar_patch_empty + 8 * ps);
-                if (last && s == p.nslab - 1) umma_commit_2sm(bar_acc_full + 8 * buf);
               }
-              __syncwarp();
-              acc0 = 1;
-              if (++bs == kB2Stages) { bs = 0; bph ^= 1; }
+              umma_commit_2sm(bar_b_empty + 8 * st);
+              if (t == TP::NT - 1) {
+                umma_commit_2sm(bar_patch_empty + 8 * ps);
+                if (last_slab) umma_commit_2sm(bar_acc_full + 8 * buf);
+              }
             }
-          }
+            __syncwarp();
+          });
+          acc0 = 1;
+          slab_par ^= (uint32_t)(kUsesPerSlab & 1);
           if (++ps == p.npb) { ps = 0; pph ^= 1; }
         }
         if (FUSE) {
@@ -783,11 +881,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         }
       }
       if (FUSE) service(true);
+#ifdef CODON_TC_EXPERIMENT
+      if (prof && cluster_id == 0 && lane == 0)
+        printf("conv_tc2<%d,%d,%d,%d> issuer: %d taps, cycles/tap: total %.0f, of which b_full wait %.0f\n",
+               NACC, OPERAND, (int)FUSE, KIND, n_taps, (double)(clock64() - c_all) / n_taps, (double)c_wait / n_taps);
+#endif
     }
   } else {
     // ================================ epilogue (both CTAs, own tile) ==============================
-    const int q = warp & 3;
-    const int ehalf = (warp - 2) >> 2;
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int ehalf = warp >> 2;                 // 0 / 1: which half of the chunks this warp drains
     const int m = q * 32 + lane;
     const int my = m / kTcSubW, mx = m % kTcSubW;
     const uint32_t acc_empty_leader = mapa_u32(bar_acc_empty, 0);
@@ -806,12 +909,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         // (64 columns at the start of the same accumulator; this warp: 32 of them) -> (+ res2) -> out2
         auto stage_y = [&](int j) {
           uint32_t ra[32], rb[32];
+          if (!TC2_DBG(p, 32)) {
           tmem_ld32(lane_base + (uint32_t)(j * 128 + ehalf * 64), ra);
           tmem_ld32(lane_base + (uint32_t)(j * 128 + ehalf * 64 + 32), rb);
           tmem_ld_wait();
+          }
           const uint32_t row = s_y + (uint32_t)ehalf * 16384u + (uint32_t)m * 128u;
 #pragma unroll
           for (int pc = 0; pc < 8; ++pc) {
+            if (TC2_DBG(p, 32)) break;
             const uint32_t* r = pc < 4 ? ra : rb;
             const int e0 = (pc & 3) * 8;
             uint32_t w[4];
@@ -826,10 +932,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         };
         auto drain_d2 = [&](int j) {
           uint32_t r[32];
+          if (TC2_DBG(p, 32)) return;
           tmem_ld32(lane_base + (uint32_t)(j * 128 + ehalf * 32), r);
           tmem_ld_wait();
           const int py = tl.y0 + (j / G::NAX) * kTcSubH + my, px = tl.x0 + (j % G::NAX) * kTcSubW + mx;
-          if (tl.valid && (py < p.H) && (px < p.W)) {
+          if (tl.valid && (py < p.H) && (px < p.W) && !TC2_DBG(p, 1)) {
             const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
             TcJob o2 = job;
             o2.out = job.out2; o2.out_stride = job.out2_stride; o2.out_off = job.out2_off;
@@ -863,7 +970,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         auto drain = [&](int i, const uint32_t (&r)[32]) {
           const int j = i >> cpa_sh, c0 = (i - (j << cpa_sh)) << 5;
           const int py = tl.y0 + (j / G::NAX) * kTcSubH + my, px = tl.x0 + (j % G::NAX) * kTcSubW + mx;
-          if (tl.valid && (py < p.H) && (px < p.W)) {
+          if (tl.valid && (py < p.H) && (px < p.W) && !TC2_DBG(p, 1)) {
             const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
             store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32);
           }
@@ -871,6 +978,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         // the two warps of a lane quarter take the even / odd chunks
         uint32_t ra[32], rb[32];
         int i = ehalf;
+        if (!TC2_DBG(p, 32)) {
         issue(i, ra);
 #pragma unroll 1
         while (true) {
@@ -884,6 +992,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           if (i + 4 >= nchunk) break;
           i += 4;
         }
+        }
       }
       tc_fence_before();
       mbar_arrive_cluster(acc_empty_leader + 8 * buf);
@@ -893,7 +1002,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();          // nobody frees TMEM or exits while the pair may still touch it
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -1103,7 +1212,25 @@ size_t setup_geometry(TcKParams& kp, int b_stage_bytes_total) {
   return fixed + (size_t)npb * kp.patch_stage;
 }
 
-template <int NACC, int OPERAND, bool FUSE>
+// the compile-time tap schedule of the cluster kernel must be the one the weights were packed with
+template <int KIND>
+bool plan_matches_kind(const TcConvPlan& plan) {
+  using TP = Taps<KIND>;
+  if (plan.ks != TP::KS || plan.ndx != TP::KS || plan.ndy != TP::KS || (plan.pair != 0) != (KIND == TK_PAIR)) return false;
+  if (KIND == TK_PAIR && plan.n_cols != 128) return false;
+  uint32_t off = 0;
+  for (int t = 0; t < TP::NT; ++t) {
+    const int dxi = t / TP::KS, dyi = t % TP::KS;
+    if (plan.dx_ord[dxi] != TP::dx(t) || plan.dy_ord[dyi] != TP::dy(t)) return false;
+    const uint32_t bytes = (KIND == TK_PAIR ? (TP::outer(t) ? 64u : 128u) : (uint32_t)plan.n_cols) * 128u;
+    if (plan.b_bytes[dxi][dyi] != bytes || plan.b_off[dxi][dyi] != off) return false;
+    if (KIND == TK_PAIR && off != (uint32_t)TP::units_before(t) * 8192u) return false;
+    off += bytes;
+  }
+  return plan.slab_bytes == off;
+}
+
+template <int NACC, int OPERAND, bool FUSE, int KIND>
 cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, const CUtensorMap& b0, const CUtensorMap& b1,
                          const CUtensorMap& w0, const CUtensorMap& w1, TcKParams& kp, cudaStream_t st) {
   // function attributes are per device: configure once per (kernel instantiation, device); one host thread per GPU
@@ -1113,14 +1240,15 @@ cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, con
   if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
   int num_sms = sms_of_dev[dev].load(std::memory_order_acquire);
   if (num_sms == 0) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NACC, OPERAND, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NACC, OPERAND, FUSE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     sms_of_dev[dev].store(num_sms, std::memory_order_release);
   }
   // fused mode adds the resident 1x1 weights (16 KB) and the Y staging tile (32 KB) behind the B ring
-  const size_t smem = setup_geometry<NACC>(kp, kB2Stages * kB2StageBytes + (FUSE ? 49152 : 0));
+  const size_t smem = setup_geometry<NACC>(kp, Taps<KIND>::NST * Taps<KIND>::kStageBytes + (FUSE ? 49152 : 0));
   if (!smem) return cudaErrorInvalidConfiguration;
+  if (kp.ks != Taps<KIND>::KS || (uint32_t)kp.n_cols * 64u > Taps<KIND>::kStageBytes) return cudaErrorInvalidValue;
   const int items = ((kp.tiles_per_job + 1) / 2) * kp.njobs;     // pair-tiles
   int clusters = num_sms / 2;
   if (items < clusters) clusters = items;
@@ -1130,7 +1258,7 @@ cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, con
     kp.main_tiles = split ? items - rem : items;
     kp.total_items = kp.main_tiles + (items - kp.main_tiles) * NACC;
   }
-  conv_tc2_kernel<NACC, OPERAND, FUSE><<<2 * clusters, kThreads2, smem, st>>>(tmap, tmapj1, b0, b1, w0, w1, kp);
+  conv_tc2_kernel<NACC, OPERAND, FUSE, KIND><<<2 * clusters, kThreads2, smem, st>>>(tmap, tmapj1, b0, b1, w0, w1, kp);
   return cudaGetLastError();
 }
 
@@ -1202,11 +1330,12 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, c
       kp.pool_stride = L.pool_stride ? L.pool_stride : (unsigned long long)L.B * L.H * L.W;
       const CUtensorMap& w0 = *L.wmap[0];
       const CUtensorMap& w1 = *L.wmap[L.njobs > 1 ? 1 : 0];
+      if (!plan_matches_kind<TK_5X5>(plan)) return cudaErrorInvalidValue;
 #define CODON_TC2F_DISPATCH(N)                                                          \
   switch (plan.operand) {                                                               \
-    case TC_F16: return launch_nacc2<N, TC_F16, true>(tmap, tmapj1, b0, b1, w0, w1, kp, st);   \
-    case TC_BF16: return launch_nacc2<N, TC_BF16, true>(tmap, tmapj1, b0, b1, w0, w1, kp, st); \
-    case TC_TF32: return launch_nacc2<N, TC_TF32, true>(tmap, tmapj1, b0, b1, w0, w1, kp, st); \
+    case TC_F16: return launch_nacc2<N, TC_F16, true, TK_5X5>(tmap, tmapj1, b0, b1, w0, w1, kp, st);   \
+    case TC_BF16: return launch_nacc2<N, TC_BF16, true, TK_5X5>(tmap, tmapj1, b0, b1, w0, w1, kp, st); \
+    case TC_TF32: return launch_nacc2<N, TC_TF32, true, TK_5X5>(tmap, tmapj1, b0, b1, w0, w1, kp, st); \
     default: return cudaErrorInvalidValue;                                              \
   }
       switch (L.nacc) {
@@ -1216,13 +1345,19 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, c
       }
 #undef CODON_TC2F_DISPATCH
     }
-#define CODON_TC2_DISPATCH(N)                                                           \
-  switch (plan.operand) {                                                               \
-    case TC_F16: return launch_nacc2<N, TC_F16, false>(tmap, tmapj1, b0, b1, b0, b1, kp, st);  \
-    case TC_BF16: return launch_nacc2<N, TC_BF16, false>(tmap, tmapj1, b0, b1, b0, b1, kp, st);\
-    case TC_TF32: return launch_nacc2<N, TC_TF32, false>(tmap, tmapj1, b0, b1, b0, b1, kp, st);\
-    default: return cudaErrorInvalidValue;                                              \
+#define CODON_TC2_DISPATCH_K(N, K)                                                          \
+  if (!plan_matches_kind<K>(plan)) return cudaErrorInvalidValue;                               \
+  switch (plan.operand) {                                                                      \
+    case TC_F16: return launch_nacc2<N, TC_F16, false, K>(tmap, tmapj1, b0, b1, b0, b1, kp, st);  \
+    case TC_BF16: return launch_nacc2<N, TC_BF16, false, K>(tmap, tmapj1, b0, b1, b0, b1, kp, st);\
+    case TC_TF32: return launch_nacc2<N, TC_TF32, false, K>(tmap, tmapj1, b0, b1, b0, b1, kp, st);\
+    default: return cudaErrorInvalidValue;                                                     \
   }
+#define CODON_TC2_DISPATCH(N)                                                                  \
+  if (plan.pair) { CODON_TC2_DISPATCH_K(N, TK_PAIR) }                                          \
+  else if (plan.ks == 5) { CODON_TC2_DISPATCH_K(N, TK_5X5) }                                   \
+  else if (plan.ks == 3) { CODON_TC2_DISPATCH_K(N, TK_3X3) }                                   \
+  else return cudaErrorInvalidValue;
     switch (L.nacc) {
       case 1: CODON_TC2_DISPATCH(1)
       case 2: CODON_TC2_DISPATCH(2)
@@ -1230,6 +1365,7 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, c
       default: return cudaErrorInvalidValue;
     }
 #undef CODON_TC2_DISPATCH
+#undef CODON_TC2_DISPATCH_K
   }
 #define CODON_TC_DISPATCH(N)                                                   \
   switch (plan.operand) {                                                      \
