@@ -801,7 +801,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
 #ifdef CODON_TC_EXPERIMENT
       // CODON_TC_DEBUG bit 64: cycle accounting of this warp (cluster 0 prints it when the kernel ends)
       const bool prof = (p.debug & 64) != 0;
-      long long c_wait = 0, c_all = prof ? clock64() : 0, c_t = 0;
+      long long c_wait = 0, c_acc = 0, c_blk = 0, c_all = prof ? clock64() : 0, c_t = 0;
+      unsigned long long g_all = 0;
+      if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_all));
       int n_taps = 0;
 #endif
       for (int item = cluster_id; item < total_items; item += nclusters, ++it) {
@@ -809,12 +811,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         const uint32_t outer_col = (uint32_t)p.job[tl.job].outer_col;
         const int buf = it % p.nbuf;
         const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
+#ifdef CODON_TC_EXPERIMENT
+        if (prof) c_t = clock64();
+#endif
         if (FUSE) {
           // the epilogue of the tile that last used this TMEM buffer needs our 1x1 MMAs to finish: keep serving
           while (!mbar_test(bar_acc_empty + 8 * buf, aph ^ 1)) service(false);
         } else {
           mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
         }
+#ifdef CODON_TC_EXPERIMENT
+        if (prof) c_acc += clock64() - c_t;
+#endif
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)buf * (uint32_t)NACC * n_cols;
         const int nacc_rt = tl.nacc;
@@ -876,15 +884,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           if (++ps == p.npb) { ps = 0; pph ^= 1; }
         }
         if (FUSE) {
+#ifdef CODON_TC_EXPERIMENT
+          if (prof) c_t = clock64();
+#endif
           service(true);                       // anything still pending belongs to the tile before this one
+#ifdef CODON_TC_EXPERIMENT
+          if (prof) c_blk += clock64() - c_t;
+#endif
           prev_left = tl.nacc; prev_j = 0; prev_job = tl.job; prev_d = d_base;
         }
       }
       if (FUSE) service(true);
 #ifdef CODON_TC_EXPERIMENT
-      if (prof && cluster_id == 0 && lane == 0)
-        printf("conv_tc2<%d,%d,%d,%d> issuer: %d taps, cycles/tap: total %.0f, of which b_full wait %.0f\n",
-               NACC, OPERAND, (int)FUSE, KIND, n_taps, (double)(clock64() - c_all) / n_taps, (double)c_wait / n_taps);
+      if (prof && (cluster_id % 24) == 0 && lane == 0) {
+        unsigned long long g_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+        const double cyc = (double)(clock64() - c_all);
+        printf("conv_tc2<%d,%d,%d,%d> cluster %d issuer: %d taps, cycles/tap: total %.0f, of which b_full wait %.0f, acc_empty wait %.0f, end-of-tile service %.0f; %.3f ms at %.0f MHz\n",
+               NACC, OPERAND, (int)FUSE, KIND, cluster_id, n_taps, cyc / n_taps, (double)c_wait / n_taps,
+               (double)c_acc / n_taps, (double)c_blk / n_taps, (double)(g_end - g_all) * 1e-6, cyc / (double)(g_end - g_all) * 1e3);
+      }
 #endif
     }
   } else {
