@@ -684,6 +684,8 @@ extern "C" {
 
 const char* codon_version(void) { return "codon_b200 0.1 (sm_100a)"; }
 
+int codon_selftest(void) { return tc_selftest(); }
+
 const char* codon_last_error(const codon_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 
 int codon_create(codon_ctx** out, int device, int scale, int mode) {

@@ -1310,6 +1310,46 @@ cudaError_t launch_nacc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, TcKP
 }
 }  // namespace
 
+int tc_selftest() {
+  int bad = 0;
+  const int ops[3] = {TC_F16, TC_BF16, TC_TF32};
+  for (int oi = 0; oi < 3; ++oi) {
+    const int op = ops[oi];
+    if (!plan_matches_kind<TK_3X3>(tc_make_plan(3, 64, 64, op))) bad |= 1;
+    if (!plan_matches_kind<TK_3X3>(tc_make_plan(3, 128, 64, op))) bad |= 1;
+    if (!plan_matches_kind<TK_5X5>(tc_make_plan(5, 128, 128, op))) bad |= 2;
+    if (!plan_matches_kind<TK_5X5>(tc_make_plan(5, 64, 64, op))) bad |= 2;
+    if (!plan_matches_kind<TK_PAIR>(tc_make_pair_plan(64, op))) bad |= 4;
+    if (plan_matches_kind<TK_5X5>(tc_make_pair_plan(64, op)) || plan_matches_kind<TK_PAIR>(tc_make_plan(5, 64, 128, op))) bad |= 8;
+    // packing: element (n, ci, dy, dx) of an OIHW tensor must be found at row n, K index ci % slab of block (slab, tap)
+    const TcConvPlan p = tc_make_plan(3, 128, 64, op);
+    const int es = op == TC_TF32 ? 4 : 2, cin = 128;
+    std::vector<float> w((size_t)64 * cin * 9);
+    for (size_t i = 0; i < w.size(); ++i) w[i] = (float)((int)(i % 251) - 125);      // exactly representable in every operand type
+    std::vector<uint8_t> packed;
+    tc_pack_weights(p, w.data(), packed);
+    if (packed.size() != p.total_bytes()) { bad |= 16; continue; }
+    for (int n = 0; n < 64; n += 7)
+      for (int ci = 0; ci < cin; ci += 5)
+        for (int t = 0; t < 9; ++t) {
+          const int dxi = t / 3, dyi = t % 3, s = ci / p.slab_elems, k = ci % p.slab_elems;
+          const uint8_t* block = packed.data() + (size_t)s * p.slab_bytes + p.b_off[dxi][dyi];
+          const int byte = k * es;
+          const uint8_t* src = block + (size_t)n * 128 + (size_t)(((byte >> 4) ^ (n & 7)) << 4) + (byte & 15);
+          const float want = w[(((size_t)n * cin + ci) * 3 + p.dy_ord[dyi]) * 3 + p.dx_ord[dxi]];
+          float got;
+          if (op == TC_TF32) memcpy(&got, src, 4);
+          else {
+            uint16_t u; memcpy(&u, src, 2);
+            if (op == TC_BF16) { uint32_t v = (uint32_t)u << 16; memcpy(&got, &v, 4); }
+            else { __half h; memcpy(&h, &u, 2); got = __half2float(h); }
+          }
+          if (got != want) bad |= 32;
+        }
+  }
+  return bad;
+}
+
 cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, const TcConvPlan& plan, const TcLaunch& L,
                            cudaStream_t st) {
   TcKParams kp;

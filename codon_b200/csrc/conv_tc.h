@@ -88,6 +88,11 @@ cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, i
 // 2-D tensor map over a packed weight stream (rows of 128 B, 32-row boxes) for the 2-CTA kernel.
 cudaError_t tc_encode_bmap(CUtensorMap* map, const void* base, size_t bytes);
 
+// Host-only consistency check (no GPU): every plan the engine builds must equal the compile-time tap schedule of
+// the cluster kernel it is launched with, and packed weights must land where the K-major SWIZZLE_128B image says.
+// Returns 0, or a bit per failed check.
+int tc_selftest();
+
 // tmap / tmapj1: activation tensor maps of job 0 / job 1 (the same map twice when both jobs read one buffer).
 cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, const TcConvPlan& plan, const TcLaunch& L,
                            cudaStream_t st);

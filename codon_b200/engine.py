@@ -21,7 +21,7 @@ _IO_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
 # every symbol include/codon_b200.h declares (tests/test_abi.py checks the list against the header)
 ABI_SYMBOLS = [
-    "codon_create", "codon_destroy", "codon_last_error", "codon_version", "codon_set_weight",
+    "codon_create", "codon_destroy", "codon_last_error", "codon_version", "codon_selftest", "codon_set_weight",
     "codon_finalize_weights", "codon_workspace_bytes", "codon_forward", "codon_forward_host",
     "codon_last_launch_count", "codon_debug_tap", "codon_profile_enable", "codon_profile_read",
     "codon_profile_reset", "codon_profile_category_name", "codon_cac_channel", "codon_cac_spatial",
@@ -59,6 +59,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         lib.codon_destroy.restype = None
         lib.codon_last_error.argtypes = [vp]
         lib.codon_last_error.restype = c.c_char_p
+        lib.codon_selftest.argtypes = []
+        lib.codon_selftest.restype = c.c_int
         lib.codon_version.argtypes = []
         lib.codon_version.restype = c.c_char_p
         lib.codon_set_weight.argtypes = [vp, c.c_char_p, fp, c.POINTER(c.c_int64), ip]
@@ -96,7 +98,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         lib.codon_group_last_ms.restype = c.c_double
         for name in ABI_SYMBOLS:
             fn = getattr(lib, name)
-            if name not in ("codon_destroy", "codon_last_error", "codon_version", "codon_workspace_bytes",
+            if name not in ("codon_destroy", "codon_last_error", "codon_version", "codon_selftest", "codon_workspace_bytes",
                             "codon_profile_category_name", "codon_group_destroy", "codon_group_last_error",
                             "codon_group_last_ms"):
                 fn.restype = c.c_int

@@ -66,6 +66,9 @@ int codon_create(codon_ctx** out, int device, int scale, int mode);
 void codon_destroy(codon_ctx* ctx);
 const char* codon_last_error(const codon_ctx* ctx);   /* ctx may be NULL: last global error */
 const char* codon_version(void);
+/* Host-only consistency check of the weight packing and of the compile-time tap schedules of the convolution kernels
+ * (no GPU needed).  Returns 0 when everything agrees, otherwise one bit per failed check. */
+int codon_selftest(void);
 
 /* Replaces: model.load_state_dict(...)  (CODON_X4/test.py:59, CODON_X16/test.py:60).
  * name is the reference state_dict key ("conv3.weight", "attention_c0.mlp.1.bias", ...; a

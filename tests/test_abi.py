@@ -29,6 +29,12 @@ def test_library_exports_every_declared_symbol(lib):
     assert b"sm_100a" in lib.codon_version()
 
 
+def test_host_selftest_weight_packing_and_tap_schedules(lib):
+    # host code only: the packed K-major SWIZZLE_128B weight image and the compile-time tap schedule of every
+    # cluster-kernel kind agree with the plans the engine builds
+    assert lib.codon_selftest() == 0
+
+
 def test_no_torch_types_in_signatures():
     src = open(os.path.join(ROOT, "include", "codon_b200.h")).read()
     assert "torch" not in re.sub(r"/\*.*?\*/", "", src, flags=re.S).lower()
