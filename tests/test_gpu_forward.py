@@ -111,6 +111,26 @@ def test_ragged_and_tiny_shapes():
         assert float((outb - ref).abs().max()) <= 1e-3, (h, w)
 
 
+def test_cluster_kernels_ragged_frame_odd_tile_count():
+    """203 x 331: large enough for the 2-CTA cluster kernels (>= 148 tiles per job), ragged in both directions
+    (partial sub-tiles, TMA zero fill on every border) and with an ODD tile count per job (the peer CTA of the last
+    pair recomputes a tile and stores nothing); the fusion stages fall to one accumulator per tile (NACC = 1)."""
+    sd = orc.synthetic_state_dict(4, 1)
+    x, y = orc.synthetic_frames(3, 203, 331, 77)
+    with torch.no_grad():
+        ref = orc.forward(sd, x[1:2].double(), y[1:2].double()).float()
+    for mode, tol in (("fp16", 1e-3), ("tf32", 1e-3), ("bf16", 2e-2)):
+        net = _net(4, 1, mode)
+        with torch.no_grad():
+            single = net(x[1:2].cuda(), y[1:2].cuda()).clone()
+            full = net(x.cuda(), y.cuda()).clone()
+        err = float((single.cpu() - ref).abs().max())
+        print(f"203x331 {mode}: {err:.3e}")
+        assert err <= tol, (mode, err)
+        # a different batch size changes the tile -> CTA schedule and the tail split, never the bits of a frame
+        assert torch.equal(full[1:2], single), mode
+
+
 def test_host_entry_point_matches_device_entry_point():
     sd = orc.synthetic_state_dict(4, 0)
     x, y = orc.synthetic_frames(2, 33, 47, 5)
