@@ -903,7 +903,15 @@ int codon_forward_host(codon_ctx* ctx, const float* depth, const float* guide, f
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t P = (size_t)B * H * W;
   if (!ctx->host_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
-  if (ctx->pin_elems < P) {
+  // Buffers the caller already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used directly;
+  // pageable ones are staged through the context's pinned buffers (one extra host memcpy each way).
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  const bool pin_d = is_pinned(depth), pin_g = is_pinned(guide), pin_o = is_pinned(out);
+  if ((!pin_d || !pin_g || !pin_o) && ctx->pin_elems < P) {
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     ctx->pin_in = ctx->pin_out = nullptr; ctx->pin_elems = 0;
@@ -927,16 +935,18 @@ int codon_forward_host(codon_ctx* ctx, const float* depth, const float* guide, f
     ctx->host_ws_bytes = need;
   }
   cudaStream_t st = ctx->host_stream;
-  memcpy(ctx->pin_in, depth, P * sizeof(float));
-  memcpy(ctx->pin_in + P, guide, P * sizeof(float));
-  CU_TRY(ctx, cudaMemcpyAsync(ctx->dev_x, ctx->pin_in, P * sizeof(float), cudaMemcpyHostToDevice, st));
-  CU_TRY(ctx, cudaMemcpyAsync(ctx->dev_y, ctx->pin_in + P, P * sizeof(float), cudaMemcpyHostToDevice, st));
+  const float* src_d = depth;
+  const float* src_g = guide;
+  if (!pin_d) { memcpy(ctx->pin_in, depth, P * sizeof(float)); src_d = ctx->pin_in; }
+  if (!pin_g) { memcpy(ctx->pin_in + P, guide, P * sizeof(float)); src_g = ctx->pin_in + P; }
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->dev_x, src_d, P * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->dev_y, src_g, P * sizeof(float), cudaMemcpyHostToDevice, st));
   int rc = codon_forward(ctx, ctx->dev_x, ctx->dev_y, ctx->dev_o, B, H, W, CODON_DTYPE_F32, ctx->host_ws,
                          ctx->host_ws_bytes, st);
   if (rc) return rc;
-  CU_TRY(ctx, cudaMemcpyAsync(ctx->pin_out, ctx->dev_o, P * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaMemcpyAsync(pin_o ? out : ctx->pin_out, ctx->dev_o, P * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaStreamSynchronize(st));
-  memcpy(out, ctx->pin_out, P * sizeof(float));
+  if (!pin_o) memcpy(out, ctx->pin_out, P * sizeof(float));
   return CODON_OK;
 }
 

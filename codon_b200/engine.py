@@ -204,9 +204,16 @@ class Engine:
 
     __call__ = forward
 
-    def forward_host(self, depth, guide):
+    @staticmethod
+    def pinned_frames(*shape):
+        """A page-locked float32 numpy array (torch pin_memory): forward_host copies such buffers to / from the
+        device directly instead of staging them through the context's own pinned buffers."""
+        return torch.empty(*shape, dtype=torch.float32, pin_memory=True).numpy()
+
+    def forward_host(self, depth, guide, out=None):
         """HOST float32 numpy arrays [B,H,W] (or [B,1,H,W]) in, numpy out; copies included
-        (the reference's H2D / D2H around the model call, CODON_X4/test.py:122-128)."""
+        (the reference's H2D / D2H around the model call, CODON_X4/test.py:122-128).  `out` may be a
+        preallocated (ideally page-locked, see pinned_frames) array of the input shape."""
         import numpy as np
         d = np.ascontiguousarray(depth, dtype=np.float32)
         g = np.ascontiguousarray(guide, dtype=np.float32)
@@ -215,7 +222,10 @@ class Engine:
         shp = d.shape
         H, W = shp[-2], shp[-1]
         B = int(d.size // (H * W))
-        out = np.empty_like(d)
+        if out is None:
+            out = np.empty_like(d)
+        elif out.dtype != np.float32 or out.shape != d.shape or not out.flags.c_contiguous:
+            raise CodonError("out must be a C-contiguous float32 array of the input shape")
         with self._lock:
             check(self.lib.codon_forward_host(self._ctx, d.ctypes.data, g.ctypes.data, out.ctypes.data, B, H, W), self._ctx)
         return out

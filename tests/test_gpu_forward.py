@@ -141,6 +141,14 @@ def test_host_entry_point_matches_device_entry_point():
     host = eng.forward_host(x.numpy(), y.numpy())
     np.testing.assert_array_equal(host, dev)
     assert eng.last_launch_count >= 30
+    # page-locked caller buffers are copied directly (no staging): same bits
+    xp, yp, op = (engine.Engine.pinned_frames(*x.shape) for _ in range(3))
+    xp[...] = x.numpy()
+    yp[...] = y.numpy()
+    assert eng.forward_host(xp, yp, out=op) is op
+    np.testing.assert_array_equal(op, dev)
+    with pytest.raises(engine.CodonError):
+        eng.forward_host(xp, yp, out=np.empty((1, 2, 3), np.float32))
 
 
 def test_errors_are_loud():
