@@ -61,6 +61,8 @@ struct TcLayer {
 struct Buffers {
   // byte offsets into the workspace
   size_t xf = 0, yf = 0, of32 = 0, E = 0, F = 0, MS = 0, R2 = 0, FUSE = 0, OF = 0, pooled = 0, part = 0, sc = 0;
+  size_t cstat = 0, cstat_half = 0;   // per-cell channel partials of the two branches (fused conv epilogue), bytes of one
+  int cells = 0;                      // 8 x 16-pixel cells per frame
   size_t total = 0;
   size_t px = 0;      // pixels the layout was planned for (B*H*W; the band mode plans every GPU for the tallest band)
   int chunks = 0;
@@ -169,6 +171,9 @@ Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W, int part_chunks 
   b.chunks = cac_stats_chunks(B, H, W);
   b.part = take((size_t)B * (part_chunks > b.chunks ? part_chunks : b.chunks) * 256 * 4);
   b.sc = take((size_t)B * 64 * 4);
+  b.cells = cdiv(W, kTcSubW) * cdiv(H, kTcSubH);
+  b.cstat_half = align_up((size_t)B * b.cells * 256 * sizeof(float2), 1024);
+  b.cstat = take(2 * b.cstat_half);
   b.total = off + 1024;   // slack for aligning the caller's pointer
   return b;
 }
@@ -317,7 +322,8 @@ struct Runner {
   // conv5x5 128->128 (+ReLU) immediately followed by conv1x1 128->64 (no ReLU, optional residual) as one
   // cluster kernel (conv_tc.cu, FUSE).  Returns 1 if the fused path is not applicable (caller falls back).
   struct FusedJob { const char* w5; const char* w1; size_t in_add; size_t out2; int out2_stride, out2_off;
-                    size_t res2; int res2_stride, res2_off; bool has_res; size_t pool; bool has_pool; };
+                    size_t res2; int res2_stride, res2_off; bool has_res; size_t pool; bool has_pool;
+                    size_t cstat = 0; bool has_cstat = false; };
   int conv5_fused(size_t in, const FusedJob* jobs, int njobs) {
     static int env = -2;
     if (env == -2) { const char* e = getenv("CODON_TC_FUSE"); env = e ? atoi(e) : 1; }
@@ -342,6 +348,7 @@ struct Runner {
       L.job[i].res2 = jobs[i].has_res ? ws + jobs[i].res2 : nullptr;
       L.job[i].res2_stride = jobs[i].res2_stride; L.job[i].res2_off = jobs[i].res2_off;
       L.job[i].pool = jobs[i].has_pool ? reinterpret_cast<float2*>(ws + jobs[i].pool) : nullptr;
+      L.job[i].cstat = jobs[i].has_cstat ? reinterpret_cast<float2*>(ws + jobs[i].cstat) : nullptr;
       L.bmap[i] = &l.bmap;
       L.wmap[i] = &l1.bmap;
       int rc = get_tmap(ctx, ws + in + jobs[i].in_add, 128, tc_box_w(l0.plan, nacc), tc_box_h(l0.plan, nacc),
@@ -449,9 +456,17 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     if ((rc = halo({bf.MS, bf.MS + half}, 128))) return rc;
     const size_t pmap = bf.px * 8;                 // bytes of one per-pixel float2 partial map
     int pool_parts = 1;
+    bool fj_cstat = false;
     {
       Runner::FusedJob fj[2] = {{"conv3", "confuse", 0, bf.F, 128, 0, 0, 0, 0, false, bf.pooled, true},
                                 {"conv6", "confuse_c", half, bf.F, 128, 64, 0, 0, 0, false, bf.pooled + 2 * pmap, true}};
+      static int use_cstat = -1;   // CODON_TC_CSTAT=0: perf experiments, stand-alone statistics pass instead
+      if (use_cstat < 0) { const char* e = getenv("CODON_TC_CSTAT"); use_cstat = e ? atoi(e) : 1; }
+      if (!hook && use_cstat) {   // the epilogue also leaves the per-cell channel partials of the global pools (not in band mode)
+        fj[0].cstat = bf.cstat; fj[0].has_cstat = true;
+        fj[1].cstat = bf.cstat + bf.cstat_half; fj[1].has_cstat = true;
+        fj_cstat = true;
+      }
       rc = r.conv5_fused(bf.MS, fj, 2);
       if (rc < 0) return rc;
       if (rc == 0) pool_parts = 4;
@@ -478,13 +493,19 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     float* sc = reinterpret_cast<float*>(ws + bf.sc);
     // algorithmic HBM bytes: stats reads F (128e B/px); apply reads F and E, writes F (384e B/px)
     if (!hook) {
-      {
+      int chunks = bf.chunks;
+      if (pool_parts == 4 && fj_cstat) {
+        // fused conv path: fold the epilogue's per-cell partials (32 B per pixel) instead of re-reading F
+        chunks = cac_cell_chunks(bf.cells);
+        ProfScope ps(ctx, PC_CAC_STATS, P * 32, st);
+        CU_TRY(ctx, launch_cac_cell_reduce(ws + bf.cstat, ws + bf.cstat + bf.cstat_half, B, bf.cells, part, chunks, st));
+      } else {
         ProfScope ps(ctx, PC_CAC_STATS, P * 128 * r.e, st);
         if (tc_mode) CU_TRY(ctx, launch_cac_chan_stats(ws + bf.F, ctx->act, B, H, W, part, bf.chunks, st));
         else CU_TRY(ctx, launch_cac_stats(ws + bf.F, ctx->act, B, H, W, pooled, part, bf.chunks, st));
       }
       ProfScope ps(ctx, PC_CAC_MLP, 0.0, st);
-      CU_TRY(ctx, launch_cac_mlp(part, bf.chunks, B, H * W, ctx->cac_w1[s], ctx->cac_b1[s], ctx->cac_w2[s],
+      CU_TRY(ctx, launch_cac_mlp(part, chunks, B, H * W, ctx->cac_w1[s], ctx->cac_b1[s], ctx->cac_w2[s],
                                  ctx->cac_b2[s], sc, st));
     } else {
       // band mode (B == 1): statistics over this band's core rows only, into its slot of the gathered buffer;

@@ -179,6 +179,31 @@ __global__ void __launch_bounds__(256, 4) cac_chan_stats_kernel(const T* __restr
   }
 }
 
+// Tensor-core modes with the fused 5x5 + 1x1 kernel: the conv epilogue already left per-channel (sum, max) partials
+// per 8 x 16-pixel cell and TMEM lane quarter (TcJob::cstat: [frame][cell][4][64] float2 per branch).  This kernel
+// folds kCellsPerChunk consecutive cells (row-major cell order of the frame) into one chunk of the `part` layout the
+// MLP kernel reduces, in a fixed order; thread = F channel (depth 0..63 from cstat_d, colour 64..127 from cstat_c).
+// It reads 32 B per pixel instead of the 128 * e B per pixel the stand-alone statistics pass re-reads from F.
+constexpr int kCellsPerChunk = 8;
+__global__ void __launch_bounds__(128) cac_cell_reduce_kernel(const float2* __restrict__ cstat_d,
+                                                              const float2* __restrict__ cstat_c, int cells,
+                                                              int chunks, float* __restrict__ part) {
+  const int b = blockIdx.y, chunk = blockIdx.x, ch = threadIdx.x;
+  const float2* src = (ch < 64 ? cstat_d : cstat_c) + (size_t)b * cells * 256 + (ch & 63);
+  const int c0 = chunk * kCellsPerChunk, c1 = min(c0 + kCellsPerChunk, cells);
+  float s = 0.f, m = -INFINITY;
+  for (int c = c0; c < c1; ++c) {
+    float2 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = __ldg(src + ((size_t)c * 4 + q) * 64);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { s += v[q].x; m = fmaxf(m, v[q].y); }
+  }
+  float* dst = part + ((size_t)(b * chunks + chunk) * 2) * 128;
+  dst[ch] = s;
+  dst[128 + ch] = m;
+}
+
 // One CTA per frame, 1024 threads.  F channel c (depth 0..63 | colour 64..127) is Fcat channel
 // (c + 64) % 128 (Fcat = [colour | depth], CODON_x4.py:85); w1 is indexed by Fcat channel.
 // The chunk partials ([chunks][sum 128 | max 128]) are reduced in a fixed order -- 16 interleaved groups of
@@ -339,6 +364,15 @@ cudaError_t launch_cac_chan_stats(const void* F, int act, int B, int H, int W, f
   if (act == ACT_F32) cac_chan_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)F, HW, chunks, part);
   else if (act == ACT_BF16) cac_chan_stats_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)F, HW, chunks, part);
   else cac_chan_stats_kernel<__half><<<grid, 256, 0, st>>>((const __half*)F, HW, chunks, part);
+  return cudaGetLastError();
+}
+
+int cac_cell_chunks(int cells) { return cdiv(cells, kCellsPerChunk); }
+
+cudaError_t launch_cac_cell_reduce(const void* cstat_d, const void* cstat_c, int B, int cells, float* part, int chunks,
+                                   cudaStream_t st) {
+  cac_cell_reduce_kernel<<<dim3(chunks, B), 128, 0, st>>>(static_cast<const float2*>(cstat_d), static_cast<const float2*>(cstat_c),
+                                                            cells, chunks, part);
   return cudaGetLastError();
 }
 

@@ -78,6 +78,7 @@ struct TcKParams {
   uint32_t idesc_1x1;            // fused 1x1: kind::f16, M = 256, N = 64
   int fuse_njobs;
   unsigned long long pool_stride;   // fused mode: pixels between the two half-channel pool maps of a job
+  int cells_x, cells_y;             // fused mode: 8 x 16-pixel cells per frame (TcJob::cstat)
   int debug;   // CODON_TC_DEBUG bits (perf experiments only; results are garbage): 1 no epilogue stores, 2 no B loads, 4 no A loads,
                // 8 no MMAs (1-CTA), 16 no waits (1-CTA), 32 no epilogue TMEM loads / Y staging (cluster kernel)
 };
@@ -969,6 +970,32 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
               job.pool[(size_t)ehalf * (size_t)p.pool_stride + pix] = make_float2(mxv, sacc);
             }
           }
+          if (job.cstat && tl.valid && tl.y0 + (j / G::NAX) * kTcSubH < p.H && tl.x0 + (j % G::NAX) * kTcSubW < p.W) {
+            // Per-channel (sum, max) over this warp's 32 pixels: a fixed-order butterfly in which the lanes that
+            // differ in bit k exchange the half of the channels they do not keep; lane l ends with channel l.
+            const bool live = (py < p.H) && (px < p.W);
+            float sv[32], mv[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float v = __uint_as_float(r[e]);
+              sv[e] = live ? v : 0.f;
+              mv[e] = live ? v : -INFINITY;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+              const bool hi = (lane & off) != 0;
+#pragma unroll
+              for (int e = 0; e < off; ++e) {
+                const float ks = hi ? sv[off + e] : sv[e], gs = hi ? sv[e] : sv[off + e];
+                const float km = hi ? mv[off + e] : mv[e], gm = hi ? mv[e] : mv[off + e];
+                sv[e] = ks + __shfl_xor_sync(0xffffffffu, gs, off);
+                mv[e] = fmaxf(km, __shfl_xor_sync(0xffffffffu, gm, off));
+              }
+            }
+            const int cy = (tl.y0 + (j / G::NAX) * kTcSubH) / kTcSubH, cx = (tl.x0 + (j % G::NAX) * kTcSubW) / kTcSubW;
+            const size_t cell = ((size_t)tl.n * p.cells_y + cy) * p.cells_x + cx;
+            job.cstat[(cell * 4 + q) * 64 + ehalf * 32 + lane] = make_float2(sv[0], mv[0]);
+          }
         };
         // Y is free here: the previous hand-off's y_done was awaited before its drain
         stage_y(0);
@@ -1387,6 +1414,7 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, c
       kp.idesc_1x1 = make_idesc(L.y16_operand, 64, 256);
       kp.fuse_njobs = L.njobs;
       kp.pool_stride = L.pool_stride ? L.pool_stride : (unsigned long long)L.B * L.H * L.W;
+      kp.cells_x = cdiv(L.W, kTcSubW); kp.cells_y = cdiv(L.H, kTcSubH);
       const CUtensorMap& w0 = *L.wmap[0];
       const CUtensorMap& w1 = *L.wmap[L.njobs > 1 ? 1 : 0];
       if (!plan_matches_kind<TK_5X5>(plan)) return cudaErrorInvalidValue;

@@ -56,6 +56,10 @@ struct TcJob {
   const void* res2 = nullptr; int res2_stride = 0; int res2_off = 0;
   float2* pool;                // optional (64-column launches, 1-CTA kernel): per-pixel (max, sum) over this job's
                                // 64 output channels -> pool[pixel]; the CAC ChannelPool partial (CAC_module.py:78-81)
+  // fused mode, optional: per-channel (sum, max) of out2 over the 32 pixels of every epilogue warp -- the partials of
+  // CAC_channel's global average / max pool (CAC_module.py:43,47).  Layout: [frame][cell_y][cell_x][lane quarter 4]
+  // [channel 64] float2, one cell = one 8 x 16-pixel sub-tile (cells_x = ceil(W / 8), cells_y = ceil(H / 16)).
+  float2* cstat = nullptr;
 };
 
 struct TcLaunch {

@@ -42,6 +42,11 @@ cudaError_t launch_cac_stats(const void* F, int act, int B, int H, int W, float*
 // come from the 1x1 conv epilogues (two [B,H,W] float2 arrays, one per branch: (max, sum) over 64 channels).
 cudaError_t launch_cac_chan_stats(const void* F, int act, int B, int H, int W, float* part, int chunks,
                                   cudaStream_t st);
+// fused conv path: folds the per-cell channel partials the conv epilogue wrote (conv_tc.h, TcJob::cstat; `cells` cells
+// of 8 x 16 pixels per frame and branch) into chunks of the `part` layout; chunks = cac_cell_chunks(cells).
+int cac_cell_chunks(int cells);
+cudaError_t launch_cac_cell_reduce(const void* cstat_d, const void* cstat_c, int B, int cells, float* part, int chunks,
+                                   cudaStream_t st);
 // mlp: deterministic reduce of the partials, MLP 128->8->64 on avg and max, sigmoid -> sc [B,64].
 // w1 [8][128] indexed by Fcat channel (colour | depth, CODON_x4.py:85), b1 [8], w2 [64][8], b2 [64].
 cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const float* w1,
