@@ -698,6 +698,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   cluster_sync_all();          // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch: the kernel may start while the previous kernel of the stream is still in its tail
+  // wave.  The set-up above and the weight producer's first ring fill (weights are constants) overlap that tail; every
+  // warp that reads activations or writes results waits here until the previous grid has completed and flushed.
+  if (warp != kWarpB) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == kWarpA) {
     // ================================ A producer (both CTAs): one activation patch per slab ======
@@ -1304,8 +1308,15 @@ cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, con
     kp.main_tiles = split ? items - rem : items;
     kp.total_items = kp.main_tiles + (items - kp.main_tiles) * NACC;
   }
-  conv_tc2_kernel<NACC, OPERAND, FUSE, KIND><<<2 * clusters, kThreads2, smem, st>>>(tmap, tmapj1, b0, b1, w0, w1, kp);
-  return cudaGetLastError();
+  static int pdl = -1;         // CODON_TC_PDL=0: plain stream order (perf experiments)
+  if (pdl < 0) { const char* e = getenv("CODON_TC_PDL"); pdl = e ? atoi(e) : 1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NACC, OPERAND, FUSE, KIND>, tmap, tmapj1, b0, b1, w0, w1, kp);
 }
 
 template <int NACC, int OPERAND>
