@@ -975,15 +975,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             }
           }
           if (job.cstat && tl.valid && tl.y0 + (j / G::NAX) * kTcSubH < p.H && tl.x0 + (j % G::NAX) * kTcSubW < p.W) {
-            // Per-channel (sum, max) over this warp's 32 pixels: a fixed-order butterfly in which the lanes that
-            // differ in bit k exchange the half of the channels they do not keep; lane l ends with channel l.
+            // Per-channel (sum, max) over this warp's 32 pixels.  Sum: a fixed-order butterfly in which the lanes that
+            // differ in bit k exchange the half of the channels they do not keep (31 shuffles; lane l ends with channel
+            // l).  Max: one warp-collective redux.sync.max.f32 per channel (CREDUX, uniform datapath) -- shuffles go
+            // through the shared-memory crossbar, which the MMA operand reads already keep ~80 % busy.
             const bool live = (py < p.H) && (px < p.W);
-            float sv[32], mv[32];
+            float sv[32];
+            float mv0 = -INFINITY;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               const float v = __uint_as_float(r[e]);
               sv[e] = live ? v : 0.f;
-              mv[e] = live ? v : -INFINITY;
+              float red;
+              asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(red) : "f"(live ? v : -INFINITY));
+              if (lane == e) mv0 = red;
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -991,11 +996,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
 #pragma unroll
               for (int e = 0; e < off; ++e) {
                 const float ks = hi ? sv[off + e] : sv[e], gs = hi ? sv[e] : sv[off + e];
-                const float km = hi ? mv[off + e] : mv[e], gm = hi ? mv[e] : mv[off + e];
                 sv[e] = ks + __shfl_xor_sync(0xffffffffu, gs, off);
-                mv[e] = fmaxf(km, __shfl_xor_sync(0xffffffffu, gm, off));
               }
             }
+            float mv[1] = {mv0};
             const int cy = (tl.y0 + (j / G::NAX) * kTcSubH) / kTcSubH, cx = (tl.x0 + (j % G::NAX) * kTcSubW) / kTcSubW;
             const size_t cell = ((size_t)tl.n * p.cells_y + cy) * p.cells_x + cx;
             job.cstat[(cell * 4 + q) * 64 + ehalf * 32 + lane] = make_float2(sv[0], mv[0]);
