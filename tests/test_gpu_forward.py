@@ -131,6 +131,28 @@ def test_cluster_kernels_ragged_frame_odd_tile_count():
         assert torch.equal(full[1:2], single), mode
 
 
+def test_random_shapes_deterministic_batch_invariant_and_close_to_fp32_mode():
+    """A short version of tools/gpu_stress.py: random frame shapes and batch sizes through the cluster kernels; every
+    case is finite, bit-reproducible, batch-invariant and within tolerance of the fp32 FFMA mode."""
+    rng = np.random.default_rng(7)
+    nets = {m: _net(4, 1, m) for m in ("fp32", "fp16", "bf16", "tf32")}
+    tol = {"fp16": 1e-3, "tf32": 1e-3, "bf16": 2e-2}
+    for _ in range(12):
+        B, H, W = int(rng.integers(1, 4)), int(rng.integers(150, 420)), int(rng.integers(150, 560))
+        x, y = orc.synthetic_frames(B, H, W, int(rng.integers(1 << 30)))
+        x, y = x.cuda(), y.cuda()
+        with torch.no_grad():
+            ref = nets["fp32"](x[:1], y[:1]).clone()
+            for mode, t in tol.items():
+                a = nets[mode](x, y).clone()
+                b = nets[mode](x, y).clone()
+                s = nets[mode](x[:1], y[:1]).clone()
+                assert torch.isfinite(a).all(), (mode, B, H, W)
+                assert torch.equal(a, b), ("nondeterministic", mode, B, H, W)
+                assert torch.equal(a[:1], s), ("batch variance", mode, B, H, W)
+                assert float((s - ref).abs().max()) <= t, (mode, B, H, W)
+
+
 def test_host_entry_point_matches_device_entry_point():
     sd = orc.synthetic_state_dict(4, 0)
     x, y = orc.synthetic_frames(2, 33, 47, 5)

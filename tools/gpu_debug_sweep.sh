@@ -1,4 +1,6 @@
 #!/bin/bash
+# Needs an experiment build of the library (tools/build_variant.sh x -DCODON_TC_EXPERIMENT, copied over
+# codon_b200/libcodon_b200.so): the knobs are compiled out of the product build.
 # Perf experiment (GPU box): CODON_TC_DEBUG knobs of the cluster conv kernel; prints per-kernel ms per step.
 # Results are numerically garbage for any non-zero knob; only the timing is meaningful.
 MODE=${1:-bf16}; FR=${2:-8}

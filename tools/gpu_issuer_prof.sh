@@ -1,4 +1,5 @@
 #!/bin/bash
+# Needs an experiment build of the library (tools/build_variant.sh x -DCODON_TC_EXPERIMENT).
 # Perf experiment (GPU box): cycle accounting of the cluster conv kernel's MMA issuer / weight producer warps
 # (CODON_TC_DEBUG bit 64, printed by cluster 0 of every launch); one forward per mode is enough.
 MODE=${1:-bf16}; FR=${2:-8}; DBG=${3:-64}
