@@ -14,10 +14,12 @@ for MODE in bf16 tf32; do
   ncu --set full --clock-control none --import-source on -k regex:conv_first\|conv_last -s 2 -c 2 -f -o $OUT/prof_edge_${TAG}_${MODE} $CMD > /dev/null 2>&1
   python tools/summarize_ncu.py $OUT/prof_edge_${TAG}_${MODE}.ncu-rep $OUT/${TAG}_edge_${MODE}.txt; rm -f $OUT/prof_edge_${TAG}_${MODE}.ncu-rep
 done
-python - <<EOF
-import json
-for f in ["bench_'"$TAG"'_tf32.json","bench_'"$TAG"'_bf16_x8_b8.json"]:
-    d=json.loads(open("gpurun_out/"+f).read().strip().splitlines()[-1])
-    print(f, round(d["value"],2), "e2e", round(d["e2e"]["value"],2), d["roofline"]["by_kernel_ms_per_step"], d["clocks"], d.get("parity"), d.get("cpu_baseline",{}).get("value"))
+python - $TAG <<'EOF'
+import json, sys
+tag = sys.argv[1]
+for f in [f"bench_{tag}_tf32.json", f"bench_{tag}_bf16_x8_b8.json"]:
+    d = json.loads(open("gpurun_out/" + f).read().strip().splitlines()[-1])
+    print(f, round(d["value"], 2), "e2e", round(d["e2e"]["value"], 2), d["roofline"]["by_kernel_ms_per_step"], d["clocks"],
+          d.get("parity"), d.get("cpu_baseline", {}).get("value"))
 EOF
 cat $OUT/configs_${TAG}_1gpu.jsonl | cut -c1-200
