@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libcodon_b200.so")
 SOURCES = ["api.cu", "conv_tc.cu", "conv_direct.cu", "cac.cu", "cac_nchw.cu", "edge.cu", "metrics.cu", "preproc.cu"]
 HEADERS = ["common.cuh", "kernels.h", "conv_tc.h", os.path.join("..", "..", "include", "codon_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
 
