@@ -276,10 +276,10 @@ __global__ void __launch_bounds__(1024) cac_mlp_kernel(const float* __restrict__
 constexpr int kATH = 8, kATW = 32;   // apply tile: 256 pixels
 
 template <typename T>
-__global__ void __launch_bounds__(256) cac_apply_kernel(T* __restrict__ F, const T* __restrict__ E,
-                                                        const float* __restrict__ pooled,
-                                                        const float* __restrict__ sc,
-                                                        const float* __restrict__ ws, int H, int W,
+__global__ void __launch_bounds__(256, 4) cac_apply_kernel(T* __restrict__ F, const T* __restrict__ E,
+                                                           const float* __restrict__ pooled,
+                                                           const float* __restrict__ sc,
+                                                           const float* __restrict__ ws, int H, int W,
                                                         int tiles_x, int rnd_tf32, int pool_parts, size_t part_stride) {
   constexpr int V = Act<T>::kVec, LPP = 128 / V, PH = kATH + 4, PW = kATW + 4;
   __shared__ float2 sp[PH][PW];
@@ -287,6 +287,27 @@ __global__ void __launch_bounds__(256) cac_apply_kernel(T* __restrict__ F, const
   const int b = blockIdx.y, t = threadIdx.x;
   const int ty0 = (blockIdx.x / tiles_x) * kATH, tx0 = (blockIdx.x % tiles_x) * kATW;
   const size_t fb = (size_t)b * H * W;
+  // The tile's F / E vectors do not depend on the gate: the first batch of kU + kU 16-byte loads is issued before
+  // the pooled-halo staging and the 5x5 gate convolution, so HBM is busy while the CTA computes s_s (r01h: every
+  // CTA of a wave sat in that prologue at the same time with no load in flight).  Thread t owns vector
+  // i = t + k * 256 (pixel i / LPP, 16-byte group i % LPP) for k < LPP, fetched in batches of kU.
+  constexpr int kU = 4, NB = LPP / kU;
+  uint4 rf[kU], re[kU];
+  int pix[kU];                                   // pixel index inside the frame, -1 = outside the image
+  auto fetch = [&](int bt) {
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int i = t + (bt * kU + u) * 256, g = i % LPP, px = i / LPP;
+      const int gy = ty0 + px / kATW, gx = tx0 + px % kATW;
+      pix[u] = (gy < H && gx < W) ? gy * W + gx : -1;
+      if (pix[u] >= 0) {
+        const size_t o = (fb + (size_t)pix[u]) * 128 + g * V;
+        rf[u] = *reinterpret_cast<const uint4*>(F + o);
+        re[u] = __ldg(reinterpret_cast<const uint4*>(E + o));
+      }
+    }
+  };
+  fetch(0);
   if (t < 50) sw[t] = ws[t];
   if (t >= 64 && t < 128) ssc[t - 64] = sc[b * 64 + t - 64];
   for (int i = t; i < PH * PW; i += 256) {
@@ -321,25 +342,27 @@ __global__ void __launch_bounds__(256) cac_apply_kernel(T* __restrict__ F, const
     sss[t] = sigmoidf_exact(q);
   }
   __syncthreads();
-#pragma unroll 2
-  for (int i = t; i < kATH * kATW * LPP; i += 256) {
-    const int g = i % LPP, px = i / LPP;
-    const int gy = ty0 + px / kATW, gx = tx0 + px % kATW;
-    if (gy < H && gx < W) {
-      const size_t o = (fb + (size_t)gy * W + gx) * 128 + g * V;
-      float f[V], e[V];
-      Act<T>::load(F + o, f);
-      Act<T>::load(E + o, e);
-      const float s = sss[px];
-      const int c0 = (g * V) & 63;
+#pragma unroll 1
+  for (int bt = 0; bt < NB; ++bt) {
 #pragma unroll
-      for (int j = 0; j < V; ++j) f[j] = fmaf(f[j], ssc[c0 + j] * s, e[j]);
-      if (rnd_tf32) {
+    for (int u = 0; u < kU; ++u) {
+      const int i = t + (bt * kU + u) * 256, px = i / LPP;
+      if (pix[u] >= 0) {
+        float f[V], e[V];
+        Act<T>::unpack(rf[u], f);
+        Act<T>::unpack(re[u], e);
+        const float s = sss[px];
+        const int c0 = ((i % LPP) * V) & 63;
 #pragma unroll
-        for (int j = 0; j < V; ++j) f[j] = round_tf32(f[j]);
+        for (int j = 0; j < V; ++j) f[j] = fmaf(f[j], ssc[c0 + j] * s, e[j]);
+        if (rnd_tf32) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) f[j] = round_tf32(f[j]);
+        }
+        Act<T>::store(F + (fb + (size_t)pix[u]) * 128 + (i % LPP) * V, f);
       }
-      Act<T>::store(F + o, f);
     }
+    if (bt + 1 < NB) fetch(bt + 1);
   }
 }
 
