@@ -112,6 +112,14 @@ struct codon_ctx {
   void* host_ws = nullptr; size_t host_ws_bytes = 0;
   float *pin_in = nullptr, *pin_out = nullptr; size_t pin_elems = 0;
   float *dev_x = nullptr, *dev_y = nullptr, *dev_o = nullptr; size_t dev_elems = 0;
+
+  // codon_forward_host_submit / _wait: two device-side I/O slots, copy streams beside the compute stream
+  struct HostSlot {
+    float *x = nullptr, *y = nullptr, *o = nullptr; size_t elems = 0;
+    cudaEvent_t in_ready = nullptr, computed = nullptr, out_ready = nullptr;
+  } slot[2];
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  unsigned long long submitted = 0, waited = 0;
 };
 
 namespace {
@@ -743,6 +751,12 @@ void codon_destroy(codon_ctx* ctx) {
   if (ctx->dev_o) cudaFree(ctx->dev_o);
   if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
   if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+  for (auto& sl : ctx->slot) {
+    for (float* p : {sl.x, sl.y, sl.o}) if (p) cudaFree(p);
+    for (cudaEvent_t e : {sl.in_ready, sl.computed, sl.out_ready}) if (e) cudaEventDestroy(e);
+  }
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
   for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
@@ -921,6 +935,8 @@ int codon_forward_host(codon_ctx* ctx, const float* depth, const float* guide, f
   if (!ctx) return fail(nullptr, CODON_ERR_ARG, "codon_forward_host: ctx is NULL");
   if (!depth || !guide || !out) return fail(ctx, CODON_ERR_ARG, "codon_forward_host: NULL pointer");
   if (B < 1 || H < 1 || W < 1) return fail(ctx, CODON_ERR_ARG, "codon_forward_host: bad shape");
+  if (ctx->submitted != ctx->waited)
+    return fail(ctx, CODON_ERR_STATE, "codon_forward_host: %llu submitted call(s) not waited for", ctx->submitted - ctx->waited);
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t P = (size_t)B * H * W;
   if (!ctx->host_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
@@ -968,6 +984,69 @@ int codon_forward_host(codon_ctx* ctx, const float* depth, const float* guide, f
   CU_TRY(ctx, cudaMemcpyAsync(pin_o ? out : ctx->pin_out, ctx->dev_o, P * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaStreamSynchronize(st));
   if (!pin_o) memcpy(out, ctx->pin_out, P * sizeof(float));
+  return CODON_OK;
+}
+
+int codon_forward_host_submit(codon_ctx* ctx, const float* depth, const float* guide, float* out, int B, int H, int W) {
+  if (!ctx) return fail(nullptr, CODON_ERR_ARG, "codon_forward_host_submit: ctx is NULL");
+  if (!depth || !guide || !out) return fail(ctx, CODON_ERR_ARG, "codon_forward_host_submit: NULL pointer");
+  if (B < 1 || H < 1 || W < 1) return fail(ctx, CODON_ERR_ARG, "codon_forward_host_submit: bad shape");
+  if (ctx->submitted - ctx->waited >= 2)
+    return fail(ctx, CODON_ERR_STATE, "codon_forward_host_submit: two calls already in flight (call codon_forward_host_wait)");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (const void* p : {(const void*)depth, (const void*)guide, (const void*)out}) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess || a.type != cudaMemoryTypeHost) {
+      cudaGetLastError();
+      return fail(ctx, CODON_ERR_ARG, "codon_forward_host_submit: %p is not page-locked host memory (asynchronous copies need "
+                                      "cudaHostAlloc / cudaHostRegister / pin_memory buffers; codon_forward_host stages pageable ones)", p);
+    }
+  }
+  const size_t P = (size_t)B * H * W;
+  if (!ctx->host_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
+  if (!ctx->h2d_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+  if (!ctx->d2h_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  codon_ctx::HostSlot& sl = ctx->slot[ctx->submitted & 1];
+  // the slot's previous call (submitted - 2) has been waited for (at most two in flight): its buffers are idle
+  if (!sl.in_ready) {
+    for (cudaEvent_t* e : {&sl.in_ready, &sl.computed, &sl.out_ready}) CU_TRY(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  if (sl.elems < P) {
+    for (float** p : {&sl.x, &sl.y, &sl.o}) { if (*p) cudaFree(*p); *p = nullptr; }
+    sl.elems = 0;
+    for (float** p : {&sl.x, &sl.y, &sl.o}) CU_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(p), P * sizeof(float)));
+    sl.elems = P;
+  }
+  const size_t need = codon_workspace_bytes(ctx, B, H, W);
+  if (ctx->host_ws_bytes < need) {
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->host_stream));   // the call in flight still computes in the old workspace
+    if (ctx->host_ws) cudaFree(ctx->host_ws);
+    ctx->host_ws = nullptr; ctx->host_ws_bytes = 0;
+    CU_TRY(ctx, cudaMalloc(&ctx->host_ws, need));
+    ctx->host_ws_bytes = need;
+  }
+  // H2D on the copy-in stream (overlaps the kernels of the call before), kernels on the compute stream, D2H on the
+  // copy-out stream (overlaps the kernels of the call after); events order the three per call
+  CU_TRY(ctx, cudaMemcpyAsync(sl.x, depth, P * sizeof(float), cudaMemcpyHostToDevice, ctx->h2d_stream));
+  CU_TRY(ctx, cudaMemcpyAsync(sl.y, guide, P * sizeof(float), cudaMemcpyHostToDevice, ctx->h2d_stream));
+  CU_TRY(ctx, cudaEventRecord(sl.in_ready, ctx->h2d_stream));
+  CU_TRY(ctx, cudaStreamWaitEvent(ctx->host_stream, sl.in_ready, 0));
+  int rc = codon_forward(ctx, sl.x, sl.y, sl.o, B, H, W, CODON_DTYPE_F32, ctx->host_ws, ctx->host_ws_bytes, ctx->host_stream);
+  if (rc) return rc;
+  CU_TRY(ctx, cudaEventRecord(sl.computed, ctx->host_stream));
+  CU_TRY(ctx, cudaStreamWaitEvent(ctx->d2h_stream, sl.computed, 0));
+  CU_TRY(ctx, cudaMemcpyAsync(out, sl.o, P * sizeof(float), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  CU_TRY(ctx, cudaEventRecord(sl.out_ready, ctx->d2h_stream));
+  ctx->submitted++;
+  return CODON_OK;
+}
+
+int codon_forward_host_wait(codon_ctx* ctx) {
+  if (!ctx) return fail(nullptr, CODON_ERR_ARG, "codon_forward_host_wait: ctx is NULL");
+  if (ctx->submitted == ctx->waited) return fail(ctx, CODON_ERR_STATE, "codon_forward_host_wait: nothing submitted");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaEventSynchronize(ctx->slot[ctx->waited & 1].out_ready));
+  ctx->waited++;
   return CODON_OK;
 }
 

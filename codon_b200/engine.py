@@ -23,6 +23,7 @@ _IO_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 ABI_SYMBOLS = [
     "codon_create", "codon_destroy", "codon_last_error", "codon_version", "codon_selftest", "codon_set_weight",
     "codon_finalize_weights", "codon_workspace_bytes", "codon_forward", "codon_forward_host",
+    "codon_forward_host_submit", "codon_forward_host_wait",
     "codon_last_launch_count", "codon_debug_tap", "codon_profile_enable", "codon_profile_read",
     "codon_profile_reset", "codon_profile_category_name", "codon_cac_channel", "codon_cac_spatial",
     "codon_cac_apply", "codon_channel_stats", "codon_channel_pool", "codon_conv2d_nchw",
@@ -69,6 +70,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         lib.codon_workspace_bytes.restype = c.c_size_t
         lib.codon_forward.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, vp, c.c_size_t, vp]
         lib.codon_forward_host.argtypes = [vp, vp, vp, vp, ip, ip, ip]
+        lib.codon_forward_host_submit.argtypes = [vp, vp, vp, vp, ip, ip, ip]
+        lib.codon_forward_host_wait.argtypes = [vp]
         lib.codon_last_launch_count.argtypes = [vp]
         lib.codon_debug_tap.argtypes = [vp, c.c_char_p, vp, c.POINTER(ip), vp]
         lib.codon_profile_enable.argtypes = [vp, ip]
@@ -229,6 +232,43 @@ class Engine:
         with self._lock:
             check(self.lib.codon_forward_host(self._ctx, d.ctypes.data, g.ctypes.data, out.ctypes.data, B, H, W), self._ctx)
         return out
+
+    def submit_host(self, depth, guide, out) -> None:
+        """Non-blocking forward_host: enqueues H2D copy -> forward -> D2H copy of one call and returns.  All three
+        arrays must be page-locked C-contiguous float32 (see pinned_frames) and must not be touched until the
+        matching wait_host() returns.  At most two calls may be in flight; keeping one submitted ahead hides the
+        copies of neighbouring calls under the kernels of the current one (stream_host does that)."""
+        import numpy as np
+        for a, what in ((depth, "depth"), (guide, "guide"), (out, "out")):
+            if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags.c_contiguous:
+                raise CodonError(f"{what} must be a C-contiguous float32 numpy array (page-locked, see pinned_frames)")
+        if depth.shape != guide.shape or out.shape != depth.shape:
+            raise CodonError("depth, guide and out shapes differ")
+        H, W = depth.shape[-2], depth.shape[-1]
+        B = int(depth.size // (H * W))
+        with self._lock:
+            check(self.lib.codon_forward_host_submit(self._ctx, depth.ctypes.data, guide.ctypes.data, out.ctypes.data,
+                                                     B, H, W), self._ctx)
+
+    def wait_host(self) -> None:
+        """Blocks until the oldest submit_host() call has written its `out`."""
+        check(self.lib.codon_forward_host_wait(self._ctx), self._ctx)
+
+    def stream_host(self, calls):
+        """Runs an iterable of (depth, guide, out) page-locked triples through submit_host / wait_host with one call
+        submitted ahead, and yields each `out` as it completes (in order).  Throughput form of the reference's
+        per-image loop (CODON_X4/test.py:109-145): the H2D copy of call i+1 and the D2H copy of call i-1 run while
+        the kernels of call i do."""
+        pending = []
+        for d, g, o in calls:
+            self.submit_host(d, g, o)
+            pending.append(o)
+            if len(pending) == 2:
+                self.wait_host()
+                yield pending.pop(0)
+        while pending:
+            self.wait_host()
+            yield pending.pop(0)
 
     def capture_graph(self, B: int, H: int, W: int, dtype: torch.dtype = torch.float32) -> "GraphedForward":
         """Captures the forward for a fixed shape into a CUDA graph: one

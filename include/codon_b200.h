@@ -101,6 +101,19 @@ int codon_forward(codon_ctx* ctx, const void* depth, const void* guide, void* ou
 int codon_forward_host(codon_ctx* ctx, const float* depth, const float* guide, float* out,
                        int B, int H, int W);
 
+/* Streaming form of codon_forward_host for a sequence of calls (the per-image loop of
+ * CODON_X4/test.py:109-145, a video, a batch queue): submit enqueues H2D copy -> forward -> D2H copy
+ * and returns at once; wait blocks until the OLDEST outstanding submit has delivered `out`.  With one
+ * call submitted ahead, the copies of neighbouring calls run on their own streams under the kernels of
+ * the current one (two device-side I/O slots, one workspace; the forwards themselves stay serialised,
+ * so results are bit-identical to codon_forward_host).  depth, guide and out must be page-locked host
+ * memory (CODON_ERR_ARG otherwise) and must stay valid and untouched until the matching wait returns.
+ * At most two submits may be outstanding (CODON_ERR_STATE on a third); codon_forward_host refuses to run
+ * while any are outstanding. */
+int codon_forward_host_submit(codon_ctx* ctx, const float* depth, const float* guide, float* out,
+                              int B, int H, int W);
+int codon_forward_host_wait(codon_ctx* ctx);
+
 /* Number of kernels the last codon_forward on this context launched. */
 int codon_last_launch_count(const codon_ctx* ctx);
 

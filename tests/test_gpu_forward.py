@@ -173,6 +173,43 @@ def test_host_entry_point_matches_device_entry_point():
         eng.forward_host(xp, yp, out=np.empty((1, 2, 3), np.float32))
 
 
+def test_streaming_host_calls_match_blocking_calls():
+    """submit_host / wait_host (copies of neighbouring calls overlap the kernels): same bits as forward_host, in
+    order, for calls of different shapes (slot and workspace re-allocation in flight); call-order errors are loud."""
+    net = _net(4, 0, "bf16")
+    eng = net.engine(torch.device("cuda", 0))
+    shapes = [(1, 40, 56), (2, 33, 47), (1, 96, 130), (1, 40, 56), (3, 17, 23), (1, 96, 130), (1, 64, 64)]
+    calls, want = [], []
+    for i, (B, H, W) in enumerate(shapes):
+        x, y = orc.synthetic_frames(B, H, W, 100 + i)
+        want.append(eng.forward_host(x.numpy(), y.numpy()).copy())
+        xp, yp, op = (engine.Engine.pinned_frames(B, 1, H, W) for _ in range(3))
+        xp[...] = x.numpy()
+        yp[...] = y.numpy()
+        op[...] = -1.0
+        calls.append((xp, yp, op))
+    got = list(eng.stream_host(calls))
+    assert len(got) == len(want)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g is calls[i][2]
+        np.testing.assert_array_equal(g, w, err_msg=f"call {i} {shapes[i]}")
+    # call order
+    with pytest.raises(engine.CodonError):
+        eng.wait_host()                                              # nothing submitted
+    eng.submit_host(*calls[0])
+    eng.submit_host(*calls[1])
+    with pytest.raises(engine.CodonError):
+        eng.submit_host(*calls[2])                                   # two already in flight
+    with pytest.raises(engine.CodonError):
+        eng.forward_host(calls[0][0], calls[0][1])                   # blocking call while submits are outstanding
+    eng.wait_host()
+    eng.wait_host()
+    np.testing.assert_array_equal(calls[1][2], want[1])
+    with pytest.raises(engine.CodonError):                           # pageable buffers cannot be copied asynchronously
+        eng.submit_host(np.zeros((1, 8, 8), np.float32), np.zeros((1, 8, 8), np.float32), np.zeros((1, 8, 8), np.float32))
+    np.testing.assert_array_equal(eng.forward_host(calls[0][0], calls[0][1]), want[0])
+
+
 def test_errors_are_loud():
     net = _net(4, 0, "fp32")
     x = torch.zeros(1, 1, 8, 8)
