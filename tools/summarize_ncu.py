@@ -35,10 +35,11 @@ def report(path, out):
             for k in KEEP:
                 if k in idx:
                     f.write(f"{k:75s} {r[idx[k]]:>16s} {units[idx[k]]}\n")
-            try:
-                rd = float(r[idx["dram__bytes_read.sum"]].replace(",", ""))
-                wr = float(r[idx["dram__bytes_write.sum"]].replace(",", ""))
-                f.write(f"{'traffic = dram read + write':75s} {rd + wr:16.3f} {units[idx['dram__bytes_read.sum']]}\n")
+            try:   # ncu scales every column's unit on its own (read in Gbyte, write in Mbyte): convert before adding
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+                rd = float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * scale[units[idx["dram__bytes_read.sum"]]]
+                wr = float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * scale[units[idx["dram__bytes_write.sum"]]]
+                f.write(f"{'traffic = dram read + write':75s} {(rd + wr) / 1e6:16.3f} Mbyte\n")
             except Exception:
                 pass
 
