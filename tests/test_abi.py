@@ -79,3 +79,33 @@ def test_module_surface_matches_reference_inventory():
     assert CODON_x4.CODONNet().half().mode == "fp16"
     assert CODON_x4.CODONNet().bfloat16().mode == "bf16"
     assert CODON_x4.CODONNet().mode == "fp32"
+
+
+def _build_c_consumer(tmp_path):
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    engine.load_library()                                            # builds the library if needed
+    exe = str(tmp_path / "c_consumer")
+    libdir = os.path.join(ROOT, "codon_b200")
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_consumer.c"), "-o", exe, "-L" + libdir, "-lcodon_b200", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr                               # the header is plain C99, no C++-isms
+    return subprocess.run([exe], capture_output=True, text=True, timeout=300)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_plain_c_consumer_links_and_fails_loudly_without_gpu(tmp_path):
+    r = _build_c_consumer(tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "no device: rc=-3" in r.stdout and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_consumer_on_gpu(tmp_path):
+    r = _build_c_consumer(tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "refused as documented" in r.stdout and r.stdout.strip().endswith("ok")
