@@ -7,8 +7,8 @@ weights -- the .pth files are absent from the reference checkout) is quantised w
 EvaluationResults / ssim_exact against the label; the GPU engine does the same in each arithmetic mode with its own
 quantise / RMSE / SSIM kernels.  Prints one line per (scale, image, mode) and a summary per mode.
 
-  python tools/gpu_image_parity.py --make-ref      # CPU only: oracle outputs -> build/parity_ref/*.npy (travels with gpurun)
-  python tools/gpu_image_parity.py                 # GPU box: table (uses build/parity_ref if present, else computes)
+  python tests/checkers/image_parity_table.py --make-ref      # CPU only: oracle outputs -> build/parity_ref/*.npy (travels with gpurun)
+  python tests/checkers/image_parity_table.py                 # GPU box: table (uses build/parity_ref if present, else computes)
 """
 import json
 import os
@@ -17,7 +17,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))   # this tool is a checker (tests/-style use of the oracle)
 import codon_oracle as orc  # noqa: E402
