@@ -41,3 +41,23 @@ def test_product_arm_refuses_to_run_without_a_gpu():
         return   # covered by the GPU runs
     r = _run(SMALL)
     assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
+
+
+def test_only_checkers_import_the_oracle():
+    """oracle/ is test infrastructure: tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it; the product
+    package and the tools never do."""
+    import re
+    allowed = {os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")}
+    offenders = []
+    for d, dirs, files in os.walk(ROOT):
+        dirs[:] = [x for x in dirs if x not in (".git", "gpurun_out", "build", "__pycache__", "tests", "oracle", "baseline")]
+        for f in files:
+            p = os.path.join(d, f)
+            if f.endswith((".py", ".sh", ".cu", ".cuh", ".h", ".c")) and p not in allowed:
+                if re.search(r"import\s+codon_oracle|from\s+codon_oracle|oracle/codon_oracle", open(p, errors="replace").read()):
+                    offenders.append(os.path.relpath(p, ROOT))
+    assert offenders == []
+    # and inside bench.py the oracle is reached only from the CPU legs
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    gpu_arm = src[src.index("def run_gpu("):src.index("def main(")]
+    assert "codon_oracle" not in gpu_arm.replace("cpu_forward_sample", "")
