@@ -177,9 +177,13 @@ Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W, int part_chunks 
   b.FUSE = take(P * 64 * e); b.OF = take(P * 64 * e);
   b.pooled = take(P * 2 * 4 * 4);   // (max, mean) map, or 2 / 4 (max, sum) partial maps from the 1x1 epilogues
   b.chunks = cac_stats_chunks(B, H, W);
-  b.part = take((size_t)B * (part_chunks > b.chunks ? part_chunks : b.chunks) * 256 * 4);
-  b.sc = take((size_t)B * 64 * 4);
   b.cells = cdiv(W, kTcSubW) * cdiv(H, kTcSubH);
+  // `part` holds the chunk partials of whichever statistics path runs: 256-pixel chunks (stand-alone pass) or folded
+  // 8 x 16-pixel cells (fused conv epilogue) -- on narrow frames the cell chunks outnumber the pixel chunks
+  int max_chunks = b.chunks > part_chunks ? b.chunks : part_chunks;
+  if (cac_cell_chunks(b.cells) > max_chunks) max_chunks = cac_cell_chunks(b.cells);
+  b.part = take((size_t)B * max_chunks * 256 * 4);
+  b.sc = take((size_t)B * 64 * 4);
   b.cstat_half = align_up((size_t)B * b.cells * 256 * sizeof(float2), 1024);
   b.cstat = take(2 * b.cstat_half);
   b.total = off + 1024;   // slack for aligning the caller's pointer
@@ -295,11 +299,15 @@ struct Runner {
     const TcLayer& l0 = ctx->w_tc.at(jobs[0].w);
     TcLaunch L;
     L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = relu; L.out_act = ctx->act;
-    L.nacc = pick_nacc(B, Hdec, W, njobs, ks == 5 ? 2 : 4, "CODON_TC_NACC_CONV");
+    const bool split = ctx->mode == CODON_MODE_F16X3;
+    // split-fp16 operands: one accumulator pair (big, small) per tile, promoted chunk by chunk (conv_tc.cu)
+    L.nacc = split ? 1 : pick_nacc(B, Hdec, W, njobs, ks == 5 ? 2 : 4, "CODON_TC_NACC_CONV");
+    if (split && ks != 3) return fail(ctx, CODON_ERR_STATE, "f16x3 mode runs the 5x5 / 1x1 layers through the fused kernels only");
     for (int i = 0; i < njobs; ++i) {
       const TcLayer& l = ctx->w_tc.at(jobs[i].w);
       L.job[i].in_coff = jobs[i].in_off;
       L.job[i].w = l.dev;
+      L.job[i].descale = 1.f / l.plan.scale;
       L.job[i].out = ws + jobs[i].out; L.job[i].out_stride = jobs[i].out_stride; L.job[i].out_off = jobs[i].out_off;
       L.job[i].res = jobs[i].has_res ? ws + jobs[i].res : nullptr;
       L.job[i].res_stride = jobs[i].res_stride; L.job[i].res_off = jobs[i].res_off;
@@ -314,6 +322,7 @@ struct Runner {
       // cluster mode: the 5x5 layers (+15-20 %) and, with one patch per slab, the 3x3 layers (+30 %); the
       // stand-alone 1x1 (fallback path only) stays single-CTA: its epilogue emits the ChannelPool partials
       L.two_cta = (ks == 5 || ks == 3 || (all && !jobs[0].has_pool)) ? use_two_cta(B, Hdec, W, L.nacc) : 0;
+      if (split) L.two_cta = 1;     // the split path exists in the cluster kernel only (any frame size)
     }
     const CUtensorMap* tm[2] = {nullptr, nullptr};
     for (int i = 0; i < njobs; ++i) {
@@ -336,19 +345,24 @@ struct Runner {
     static int env = -2;
     if (env == -2) { const char* e = getenv("CODON_TC_FUSE"); env = e ? atoi(e) : 1; }
     if (ctx->mode == CODON_MODE_FP32 || !env) return 1;
-    const int nacc = pick_nacc(B, Hdec, W, njobs, 2, "CODON_TC_NACC_CONV");
-    if (nacc > 2 || !use_two_cta(B, Hdec, W, nacc)) return 1;
+    const bool split = ctx->mode == CODON_MODE_F16X3;
+    // split-fp16 operands: one accumulator per tile (four patch stages + the two-plane Y tile fill shared memory),
+    // always through this kernel
+    const int nacc = split ? 1 : pick_nacc(B, Hdec, W, njobs, 2, "CODON_TC_NACC_CONV");
+    if (!split && (nacc > 2 || !use_two_cta(B, Hdec, W, nacc))) return 1;
     const TcLayer& l0 = ctx->w_tc.at(jobs[0].w5);
     TcLaunch L;
     L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = 1; L.out_act = ctx->act;
     L.nacc = nacc; L.two_cta = 1; L.fuse = 1; L.pool_stride = px;
     L.y16_operand = ctx->mode == CODON_MODE_BF16 ? TC_BF16 : TC_F16;
+    if (split && !env) return fail(ctx, CODON_ERR_STATE, "f16x3 mode needs the fused 5x5 + 1x1 kernel (CODON_TC_FUSE=0 set)");
     const CUtensorMap* tm[2] = {nullptr, nullptr};
     for (int i = 0; i < njobs; ++i) {
       const TcLayer& l = ctx->w_tc.at(jobs[i].w5);
       const TcLayer& l1 = ctx->w_tc.at(std::string(jobs[i].w1) + "@y16");
       L.job[i].in_coff = 0;
       L.job[i].w = l.dev;
+      L.job[i].descale = 1.f / l.plan.scale; L.job[i].descale2 = 1.f / l1.plan.scale;
       L.job[i].out = nullptr; L.job[i].out_stride = 0; L.job[i].out_off = 0;
       L.job[i].res = nullptr; L.job[i].res_stride = 0; L.job[i].res_off = 0;
       L.job[i].outer_col = 0;
@@ -398,18 +412,20 @@ struct Runner {
     const TcLayer& l0 = ctx->w_tc.at(wpair[0]);
     TcLaunch L;
     L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = 1; L.out_act = ctx->act;
-    L.nacc = pick_nacc(B, Hdec, W, njobs, 2, "CODON_TC_NACC_PAIR");
+    const bool split = ctx->mode == CODON_MODE_F16X3;
+    L.nacc = split ? 1 : pick_nacc(B, Hdec, W, njobs, 2, "CODON_TC_NACC_PAIR");
     for (int i = 0; i < njobs; ++i) {
       const TcLayer& l = ctx->w_tc.at(wpair[i]);
       L.job[i].in_coff = in_off[i];
       L.job[i].w = l.dev;
+      L.job[i].descale = 1.f / l.plan.scale;
       L.job[i].out = ws + out + out_add[i]; L.job[i].out_stride = out_stride; L.job[i].out_off = out_off[i];
       L.job[i].res = nullptr; L.job[i].res_stride = 0; L.job[i].res_off = 0;
       L.job[i].outer_col = three_first[i] ? 64 : 0;
       L.job[i].pool = nullptr;
       L.bmap[i] = &l.bmap;
     }
-    L.two_cta = use_two_cta(B, Hdec, W, L.nacc);
+    L.two_cta = split ? 1 : use_two_cta(B, Hdec, W, L.nacc);
     const CUtensorMap* tm = nullptr;
     int rc = get_tmap(ctx, ws + in, in_C, tc_box_w(l0.plan, L.nacc), tc_box_h(l0.plan, L.nacc), l0.plan.slab_elems, B, H, W, &tm);
     if (rc) return rc;
@@ -721,7 +737,7 @@ int codon_create(codon_ctx** out, int device, int scale, int mode) {
   if (!out) return fail(nullptr, CODON_ERR_ARG, "codon_create: out is NULL");
   *out = nullptr;
   if (scale != 4 && scale != 8 && scale != 16) return fail(nullptr, CODON_ERR_ARG, "codon_create: scale must be 4, 8 or 16 (got %d)", scale);
-  if (mode < CODON_MODE_FP32 || mode > CODON_MODE_TF32) return fail(nullptr, CODON_ERR_ARG, "codon_create: unknown mode %d", mode);
+  if (mode < CODON_MODE_FP32 || mode > CODON_MODE_F16X3) return fail(nullptr, CODON_ERR_ARG, "codon_create: unknown mode %d", mode);
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0)
@@ -736,7 +752,7 @@ int codon_create(codon_ctx** out, int device, int scale, int mode) {
   CU_TRY(nullptr, cudaSetDevice(device));
   codon_ctx* c = new codon_ctx();
   c->device = device; c->scale = scale; c->mode = mode;
-  c->act = mode == CODON_MODE_BF16 ? ACT_BF16 : mode == CODON_MODE_FP16 ? ACT_F16 : ACT_F32;
+  c->act = mode == CODON_MODE_BF16 ? ACT_BF16 : mode == CODON_MODE_FP16 ? ACT_F16 : mode == CODON_MODE_F16X3 ? ACT_SPLIT16 : ACT_F32;
   *out = c;
   return CODON_OK;
 }
@@ -845,22 +861,29 @@ int codon_finalize_weights(codon_ctx* ctx) {
       ctx->w_direct[s.name] = d;
     }
   } else {
-    const int operand = ctx->mode == CODON_MODE_BF16 ? TC_BF16 : ctx->mode == CODON_MODE_FP16 ? TC_F16 : TC_TF32;
+    const int operand = ctx->mode == CODON_MODE_BF16 ? TC_BF16 : ctx->mode == CODON_MODE_FP16 ? TC_F16
+                        : ctx->mode == CODON_MODE_F16X3 ? TC_SPLIT16 : TC_TF32;
+    // split-fp16 operands: per-layer power-of-two weight scale (TcConvPlan::scale), undone in the epilogue
+    auto scale_of = [&](const char* a, const char* b = nullptr) {
+      if (operand != TC_SPLIT16) return 1.f;
+      const std::vector<float>& wa = W(a).data;
+      return b ? tc_pick_scale(wa.data(), wa.size(), W(b).data.data(), W(b).data.size()) : tc_pick_scale(wa.data(), wa.size());
+    };
     std::vector<uint8_t> packed;
     for (const ConvSpec& s : kTrunk) {
       if (s.cin == 1 || s.cout == 1) continue;
       TcLayer l;
-      l.plan = tc_make_plan(s.ks, s.cin, s.cout, operand);
+      l.plan = tc_make_plan(s.ks, s.cin, s.cout, operand, scale_of(s.name));
       tc_pack_weights(l.plan, W(s.name).data.data(), packed);
       if ((rc = upload(ctx, packed, &l.dev))) return rc;
       CU_TRY(ctx, tc_encode_bmap(&l.bmap, l.dev, packed.size()));
       ctx->w_tc[s.name] = l;
     }
     // 16-bit copies of the 1x1 weights for the fused conv5+1x1 kernel (fp16 in tf32 mode: same mantissa width)
-    const int y16 = operand == TC_BF16 ? TC_BF16 : TC_F16;
+    const int y16 = operand == TC_BF16 ? TC_BF16 : operand == TC_SPLIT16 ? TC_SPLIT16 : TC_F16;
     for (const char* n : {"confuse", "confuse_c", "confuse_fuse"}) {
       TcLayer l;
-      l.plan = tc_make_plan(1, 128, 64, y16);
+      l.plan = tc_make_plan(1, 128, 64, y16, scale_of(n));
       tc_pack_weights(l.plan, W(n).data.data(), packed);
       if ((rc = upload(ctx, packed, &l.dev))) return rc;
       CU_TRY(ctx, tc_encode_bmap(&l.bmap, l.dev, packed.size()));
@@ -871,7 +894,7 @@ int codon_finalize_weights(codon_ctx* ctx) {
     for (const PairSpec& p : {PairSpec{"pair_d", "conv1", "conv2", true}, PairSpec{"pair_c", "conv5", "conv4", false},
                               PairSpec{"pair_f", "conv9", "conv8", false}}) {
       TcLayer l;
-      l.plan = tc_make_pair_plan(64, operand);
+      l.plan = tc_make_pair_plan(64, operand, scale_of(p.w3, p.w5));
       tc_pack_pair_weights(l.plan, W(p.w3).data.data(), W(p.w5).data.data(), p.three_first, packed);
       if ((rc = upload(ctx, packed, &l.dev))) return rc;
       CU_TRY(ctx, tc_encode_bmap(&l.bmap, l.dev, packed.size()));

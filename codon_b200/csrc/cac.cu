@@ -27,7 +27,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 4) cac_stats_kernel(const T* __restrict__ F, int HW, int chunks,
                                                         float* __restrict__ pooled,
                                                         float* __restrict__ part) {
-  constexpr int V = Act<T>::kVec, LPP = 128 / V, PPW = 32 / LPP, kU = 8;
+  constexpr int V = Act<T>::kVec, LPP = 128 / V, PPW = 32 / LPP, kU = sizeof(typename Act<T>::Raw) > 16 ? 4 : 8;
   constexpr int ROWPX = 8 * PPW;                 // pixels covered by one load instruction of the CTA
   constexpr int NIT = kChunkPx / (ROWPX * kU);   // 2 (16-bit) or 4 (fp32) batches of kU loads
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -43,11 +43,11 @@ __global__ void __launch_bounds__(256, 4) cac_stats_kernel(const T* __restrict__
 #pragma unroll 1
   for (int it = 0; it < NIT; ++it) {
     const int p0 = p_begin + it * ROWPX * kU + warp * PPW + sub;
-    uint4 raw[kU];
+    typename Act<T>::Raw raw[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int p = p0 + u * ROWPX;
-      raw[u] = p < p_end ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * 128 + g * V)) : make_uint4(0, 0, 0, 0);
+      raw[u] = Act<T>::ldg(base + (size_t)(p < p_end ? p : p_begin) * 128 + g * V);   // out-of-range lanes are masked below
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256, 4) cac_stats_kernel(const T* __restrict__
 template <typename T> struct PackedMax;
 template <> struct PackedMax<float> {
   using Acc = uint4;
+  __device__ static inline void fin(const uint4& a, float (&m)[4]) { Act<float>::unpack(a, m); }
   __device__ static inline uint4 init() { const uint32_t n = 0xff800000u; return make_uint4(n, n, n, n); }
   __device__ static inline void upd(uint4& a, const uint4& v) {
     a.x = __float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(v.x)));
@@ -106,6 +107,8 @@ template <> struct PackedMax<float> {
   }
 };
 template <> struct PackedMax<__nv_bfloat16> {
+  using Acc = uint4;
+  __device__ static inline void fin(const uint4& a, float (&m)[8]) { Act<__nv_bfloat16>::unpack(a, m); }
   __device__ static inline uint4 init() { const uint32_t n = 0xff80ff80u; return make_uint4(n, n, n, n); }
   __device__ static inline uint32_t mx(uint32_t a, uint32_t b) {
     __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
@@ -113,7 +116,23 @@ template <> struct PackedMax<__nv_bfloat16> {
   }
   __device__ static inline void upd(uint4& a, const uint4& v) { a.x = mx(a.x, v.x); a.y = mx(a.y, v.y); a.z = mx(a.z, v.z); a.w = mx(a.w, v.w); }
 };
+template <> struct PackedMax<split16> {   // hi + lo must be recombined: the maximum is taken on the fp32 values
+  struct Acc { float m[8]; };
+  __device__ static inline Acc init() { Acc a; for (int j = 0; j < 8; ++j) a.m[j] = -INFINITY; return a; }
+  __device__ static inline void upd(Acc& a, const RawSplit& v) {
+    float f[8];
+    Act<split16>::unpack(v, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.m[j] = fmaxf(a.m[j], f[j]);
+  }
+  __device__ static inline void fin(const Acc& a, float (&m)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = a.m[j];
+  }
+};
 template <> struct PackedMax<__half> {
+  using Acc = uint4;
+  __device__ static inline void fin(const uint4& a, float (&m)[8]) { Act<__half>::unpack(a, m); }
   __device__ static inline uint4 init() { const uint32_t n = 0xfc00fc00u; return make_uint4(n, n, n, n); }
   __device__ static inline uint32_t mx(uint32_t a, uint32_t b) {
     __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
@@ -125,7 +144,7 @@ template <> struct PackedMax<__half> {
 template <typename T>
 __global__ void __launch_bounds__(256, 4) cac_chan_stats_kernel(const T* __restrict__ F, int HW, int chunks,
                                                                 float* __restrict__ part) {
-  constexpr int V = Act<T>::kVec, LPP = 128 / V, PPW = 32 / LPP, kU = 8;
+  constexpr int V = Act<T>::kVec, LPP = 128 / V, PPW = 32 / LPP, kU = sizeof(typename Act<T>::Raw) > 16 ? 4 : 8;
   constexpr int ROWPX = 8 * PPW;
   constexpr int NIT = kChunkPx / (ROWPX * kU);
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -136,18 +155,18 @@ __global__ void __launch_bounds__(256, 4) cac_chan_stats_kernel(const T* __restr
   float csum[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) csum[j] = 0.f;
-  uint4 cmax = PackedMax<T>::init();
+  typename PackedMax<T>::Acc cmax = PackedMax<T>::init();
 
 #pragma unroll 1
   for (int it = 0; it < NIT; ++it) {
     const int p0 = p_begin + it * ROWPX * kU + warp * PPW + sub;
-    uint4 raw[kU];
+    typename Act<T>::Raw raw[kU];
     bool ok[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int p = p0 + u * ROWPX;
       ok[u] = p < p_end;
-      if (ok[u]) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * 128 + g * V));
+      if (ok[u]) raw[u] = Act<T>::ldg(base + (size_t)p * 128 + g * V);
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -161,7 +180,7 @@ __global__ void __launch_bounds__(256, 4) cac_chan_stats_kernel(const T* __restr
     }
   }
   float cmx[V];
-  Act<T>::unpack(cmax, cmx);
+  PackedMax<T>::fin(cmax, cmx);
   __shared__ float rs[8 * PPW][128], rm[8 * PPW][128];
 #pragma unroll
   for (int j = 0; j < V; ++j) {
@@ -291,8 +310,8 @@ __global__ void __launch_bounds__(256, 4) cac_apply_kernel(T* __restrict__ F, co
   // the pooled-halo staging and the 5x5 gate convolution, so HBM is busy while the CTA computes s_s (r01h: every
   // CTA of a wave sat in that prologue at the same time with no load in flight).  Thread t owns vector
   // i = t + k * 256 (pixel i / LPP, 16-byte group i % LPP) for k < LPP, fetched in batches of kU.
-  constexpr int kU = 4, NB = LPP / kU;
-  uint4 rf[kU], re[kU];
+  constexpr int kU = sizeof(typename Act<T>::Raw) > 16 ? 2 : 4, NB = LPP / kU;
+  typename Act<T>::Raw rf[kU], re[kU];
   int pix[kU];                                   // pixel index inside the frame, -1 = outside the image
   auto fetch = [&](int bt) {
 #pragma unroll
@@ -302,8 +321,8 @@ __global__ void __launch_bounds__(256, 4) cac_apply_kernel(T* __restrict__ F, co
       pix[u] = (gy < H && gx < W) ? gy * W + gx : -1;
       if (pix[u] >= 0) {
         const size_t o = (fb + (size_t)pix[u]) * 128 + g * V;
-        rf[u] = *reinterpret_cast<const uint4*>(F + o);
-        re[u] = __ldg(reinterpret_cast<const uint4*>(E + o));
+        rf[u] = Act<T>::ld(F + o);
+        re[u] = Act<T>::ldg(E + o);
       }
     }
   };
@@ -376,6 +395,7 @@ cudaError_t launch_cac_stats(const void* F, int act, int B, int H, int W, float*
   const int HW = H * W;
   if (act == ACT_F32) cac_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)F, HW, chunks, pooled, part);
   else if (act == ACT_BF16) cac_stats_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)F, HW, chunks, pooled, part);
+  else if (act == ACT_SPLIT16) cac_stats_kernel<split16><<<grid, 256, 0, st>>>((const split16*)F, HW, chunks, pooled, part);
   else cac_stats_kernel<__half><<<grid, 256, 0, st>>>((const __half*)F, HW, chunks, pooled, part);
   return cudaGetLastError();
 }
@@ -386,6 +406,7 @@ cudaError_t launch_cac_chan_stats(const void* F, int act, int B, int H, int W, f
   const int HW = H * W;
   if (act == ACT_F32) cac_chan_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)F, HW, chunks, part);
   else if (act == ACT_BF16) cac_chan_stats_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)F, HW, chunks, part);
+  else if (act == ACT_SPLIT16) cac_chan_stats_kernel<split16><<<grid, 256, 0, st>>>((const split16*)F, HW, chunks, part);
   else cac_chan_stats_kernel<__half><<<grid, 256, 0, st>>>((const __half*)F, HW, chunks, part);
   return cudaGetLastError();
 }
@@ -413,6 +434,7 @@ cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* poole
   dim3 grid(tiles_x * cdiv(H, kATH), B);
   if (act == ACT_F32) cac_apply_kernel<float><<<grid, 256, 0, st>>>((float*)F, (const float*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride);
   else if (act == ACT_BF16) cac_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)F, (const __nv_bfloat16*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride);
+  else if (act == ACT_SPLIT16) cac_apply_kernel<split16><<<grid, 256, 0, st>>>((split16*)F, (const split16*)E, pooled, sc, ws, H, W, tiles_x, 0, pool_parts, part_stride);
   else cac_apply_kernel<__half><<<grid, 256, 0, st>>>((__half*)F, (const __half*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride);
   return cudaGetLastError();
 }

@@ -92,6 +92,13 @@ template <int NACC> struct Geo {
 // straight-line code per tap (descriptor offsets and byte counts are immediates).  Must match fill_orders() /
 // tc_make_plan() / tc_make_pair_plan() below (checked on the host before every launch).
 enum TcKind : int { TK_3X3 = 0, TK_5X5 = 1, TK_PAIR = 2 };
+// split-fp16 mode: taps per accumulation chunk (see conv_tc2_kernel); must divide 9 resp. 25
+#ifndef CODON_SPLIT_TPC_3X3
+#define CODON_SPLIT_TPC_3X3 1
+#endif
+#ifndef CODON_SPLIT_TPC_5X5
+#define CODON_SPLIT_TPC_5X5 1
+#endif
 template <int KIND> struct Taps {
   static constexpr int KS = KIND == TK_3X3 ? 3 : 5;
   static constexpr int NT = KS * KS;
@@ -107,6 +114,12 @@ template <int KIND> struct Taps {
   // pair plans: the 16 border taps belong to the 5x5 convolution only (64 weight rows, N = 64)
   __host__ __device__ static constexpr bool outer(int t) {
     return KIND == TK_PAIR && (dx(t) == 0 || dx(t) == 4 || dy(t) == 0 || dy(t) == 4);
+  }
+  // pair plans, split mode: bit c = accumulation chunk c (taps [c * tpc, (c + 1) * tpc)) starts with a border tap
+  __host__ __device__ static constexpr uint32_t outer_chunk_mask(int tpc) {
+    uint32_t m = 0;
+    for (int c = 0; c * tpc < NT; ++c) if (outer(c * tpc)) m |= 1u << c;
+    return m;
   }
   // pair plans: 64-row (8 KB) units of one slab's weight stream that precede tap t
   __host__ __device__ static constexpr int units_before(int t) {
@@ -221,6 +234,7 @@ template <int OPERAND> struct OperandTraits;
 template <> struct OperandTraits<TC_F16> { using Out = __half; };
 template <> struct OperandTraits<TC_BF16> { using Out = __nv_bfloat16; };
 template <> struct OperandTraits<TC_TF32> { using Out = float; };
+template <> struct OperandTraits<TC_SPLIT16> { using Out = split16; };
 
 struct Tile { int job, n, y0, x0, nacc, valid; };
 // Work item -> tile.  Full tiles hold NACC sub-tiles (NAX x NAY).  The tiles of the last, partial
@@ -262,7 +276,7 @@ __device__ __forceinline__ uint64_t desc_addr(uint32_t saddr) { return (uint64_t
 // Epilogue of one 32-channel chunk held by one thread (one pixel).
 template <typename T>
 __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], const TcJob& job, size_t pix, int c0,
-                                            bool relu, bool rnd_tf32 = false) {
+                                            bool relu, bool rnd_tf32 = false, float scale = 1.f) {
   constexpr int V = Act<T>::kVec;
   T* out = static_cast<T*>(job.out) + pix * job.out_stride + job.out_off + c0;
   const T* res = job.res ? static_cast<const T*>(job.res) + pix * job.res_stride + job.res_off + c0 : nullptr;
@@ -272,6 +286,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], const TcJob
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       f[j] = __uint_as_float(r[v * V + j]);
+      if (std::is_same<T, split16>::value) f[j] *= scale;
       if (relu) f[j] = fmaxf(f[j], 0.f);
     }
     if (res) {
@@ -589,9 +604,18 @@ template <> __device__ __forceinline__ uint32_t pack16<TC_BF16>(float lo, float 
   return *reinterpret_cast<uint32_t*>(&h);
 }
 template <> __device__ __forceinline__ uint32_t pack16<TC_F16>(float lo, float hi) {
-  __half2 h = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
+  // saturating: a post-ReLU activation above 65504 (possible with fp32 storage in the tf32 mode) clamps to the
+  // largest finite fp16 instead of turning into inf and poisoning the 1x1 product
+  return cvt_f16x2_sat(lo, hi);
 }
+
+// Split mode, fused 1x1: state of the hand-offs the MMA issuer still owes the epilogue, and their out-of-line
+// service routine (the issue loop is ~50 straight-line "uses" per slab; inlining the 12 MMAs of a hand-off into each
+// of them made the loop ~10x larger than the instruction cache and doubled the cycles per MMA).
+// All state is passed by value (it stays in the caller's registers); returns the number of hand-offs issued.
+__device__ __noinline__ int fuse_service_split(int left, int j, int job, uint32_t d, uint32_t y_uses, bool wc_ready,
+                                               uint32_t bar_y_full, uint32_t bar_y_done, uint32_t bar_wc_full,
+                                               uint32_t s_y, uint32_t s_wc, uint32_t idesc_1x1, bool block);
 
 struct Tile2 { int job, n, y0, x0, valid, nacc; };
 // Work item -> this CTA's tile.  Items [0, main_tiles) are pair-tiles (tiles 2q and 2q+1 of a job);
@@ -642,8 +666,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   constexpr int NST = TP::NST;
   constexpr uint32_t kStageBytes = TP::kStageBytes;
   static_assert(TP::NT % NST == 0 && NST <= kB2MaxStages, "ring must divide the tap count");
-  constexpr int kUsesPerSlab = TP::NT / NST;     // odd (1 or 5): the parity of a stage flips from slab to slab
+  constexpr int kUsesPerSlab = (OPERAND == TC_SPLIT16 ? 2 : 1) * TP::NT / NST;   // odd (1, 5): a stage's parity flips per slab; even (split): it does not
   constexpr int Y16 = OPERAND == TC_BF16 ? TC_BF16 : TC_F16;   // tf32 mode stages Y in fp16 (same 10-bit mantissa)
+  // Split-fp16 operands (F16X3 mode): per 64-channel slab TWO activation patches (hi, lo planes) and per tap TWO
+  // weight blocks (hi, lo) -- ring "uses" u = 2 * tap + plane -- and three MMA groups per tap: A_hi*B_hi and
+  // A_lo*B_hi on the hi block, A_hi*B_lo on the lo block, all into the same accumulator.
+  //   The tensor core truncates (round-toward-zero) the fp32 accumulator after every MMA; over the 600 MMAs of a
+  // 5x5 x 128-channel output that bias is ~40x the error of an fp32 FFMA loop (measured, and reproduced by a CPU
+  // model of RZ accumulation).  Split mode therefore keeps two kinds of TMEM accumulators:
+  //   "big"   (hi*hi) in CHUNKS of kTPC taps of one slab: a chunk starts a fresh accumulator, and the epilogue warps
+  //           promote every finished chunk to round-to-nearest fp32 running sums in registers.  Three rotating
+  //           buffers of n_cols columns (kSplitBufs): two chunks can be in flight while one is being promoted.
+  //   "small" (lo*hi + hi*lo, 2^-11 of the magnitude: its own truncation is irrelevant, and its additions no longer
+  //           truncate at the big sum's ulp) once per tile, n_cols columns behind the big buffers; read together
+  //           with the tile's last chunk and handed back through bar_small_empty.
+  constexpr bool SPLIT = OPERAND == TC_SPLIT16;
+  constexpr int NU = SPLIT ? 2 * TP::NT : TP::NT;                // weight-ring uses per slab
+  constexpr int kTPC = KIND == TK_3X3 ? CODON_SPLIT_TPC_3X3 : CODON_SPLIT_TPC_5X5;   // taps per accumulation chunk
+  constexpr int kSplitBufs = 3;
+  static_assert(TP::NT % kTPC == 0, "chunks must tile the taps of a slab");
+  static_assert(!SPLIT || NACC == 1, "split mode: one accumulator (big + small, double-buffered) per tile");
   constexpr uint32_t kPitch = (uint32_t)(G::TW + TP::KS - 1) * 128u;   // patch row pitch in bytes (== p.pw * 128)
 
   extern __shared__ uint8_t smem_raw[];
@@ -653,14 +695,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   const uint32_t s_b = s_patch + p.npb * p.patch_stage;
   const uint32_t bar_patch_full = s_bar, bar_patch_empty = s_bar + 8 * kMaxNPB;
   const uint32_t bar_b_full = s_bar + 16 * kMaxNPB, bar_b_empty = bar_b_full + 8 * kB2MaxStages;
-  const uint32_t bar_acc_full = bar_b_empty + 8 * kB2MaxStages, bar_acc_empty = bar_acc_full + 16;
-  const uint32_t bar_y_full = bar_acc_empty + 16, bar_y_done = bar_y_full + 8, bar_wc_full = bar_y_done + 8;
-  const uint32_t s_tmem_slot = bar_wc_full + 8;
+  const uint32_t bar_acc_full = bar_b_empty + 8 * kB2MaxStages, bar_acc_empty = bar_acc_full + 32;   // up to 4 TMEM buffers
+  const uint32_t bar_y_full = bar_acc_empty + 32, bar_y_done = bar_y_full + 8, bar_wc_full = bar_y_done + 8;
+  const uint32_t bar_small_empty = bar_wc_full + 8;     // split mode: the per-tile "small" accumulator has been read
+  const uint32_t s_tmem_slot = bar_small_empty + 8;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (s_tmem_slot - smem_u32(smem_raw)));
   // fused mode: [1x1 weights: 2 jobs x 2 slabs x 32 rows x 128 B = 16 KB][Y: 2 slabs x 128 rows x 128 B = 32 KB]
+  // split:      [2 jobs x 2 slabs x (hi, lo) x 32 rows x 128 B = 32 KB][Y: (hi, lo) x 128 rows x 128 B = 32 KB, ONE
+  //             64-channel slab at a time: an accumulator is handed over in two rounds]
   const uint32_t s_wc = s_b + NST * kStageBytes;
-  const uint32_t s_y = s_wc + 16384;
+  const uint32_t s_y = s_wc + (SPLIT ? 32768u : 16384u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -675,8 +720,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap1) : "memory");
     for (int i = 0; i < p.npb; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
     for (int i = 0; i < NST; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 512); }
-    mbar_init(bar_y_full, 512); mbar_init(bar_y_done, 1); mbar_init(bar_wc_full, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 512); }
+    mbar_init(bar_y_full, 512); mbar_init(bar_y_done, 1); mbar_init(bar_wc_full, 1); mbar_init(bar_small_empty, 512);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWarpMma) {
@@ -702,14 +747,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     for (int item = cluster_id; item < total_items; item += nclusters) {
       const Tile2 tl = decode_tile2<NACC>(p, item, (int)rank);
       const int coff = p.job[tl.job].in_coff;
-      for (int s = 0; s < p.nslab; ++s) {
+      const int npatch = SPLIT ? 2 * p.nslab : p.nslab;   // split: patch 2s = hi plane, 2s + 1 = lo plane of slab s
+      for (int s = 0; s < npatch; ++s) {
+        // channel coordinate in the tensor map (split: fp16 units, a slab is [64 hi | 64 lo])
+        const int ccoord = SPLIT ? 2 * coff + (s >> 1) * 128 + (s & 1) * 64 : coff + s * p.slab_elems;
         mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
         if (elect_one()) {
           if (TC2_DBG(p, 4)) { if (leader) mbar_arrive(bar_patch_full + 8 * ps); }
           else {
             if (leader) mbar_expect_tx(bar_patch_full + 8 * ps, 2 * p.patch_tx);
             tma_load_4d_2sm(s_patch + ps * p.patch_stage, tl.job ? &tmap1 : &tmap0, full_leader + 8 * ps,
-                            coff + s * p.slab_elems, tl.x0 - p.pad, tl.y0 - p.pad, tl.n);
+                            ccoord, tl.x0 - p.pad, tl.y0 - p.pad, tl.n);
           }
         }
         __syncwarp();
@@ -722,12 +770,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     const uint32_t full_leader = mapa_u32(bar_b_full, 0);
     if (FUSE && elect_one()) {
       // resident 1x1 weights: this CTA's 32 of the 64 output rows, per job and 128-byte K slab
-      if (leader) mbar_expect_tx(bar_wc_full, (uint32_t)p.fuse_njobs * 2u * 8192u);
+      constexpr uint32_t kPl = SPLIT ? 2u : 1u;      // planes per slab of the 1x1 stream: [hi 64 rows][lo 64 rows]
+      if (leader) mbar_expect_tx(bar_wc_full, (uint32_t)p.fuse_njobs * 2u * kPl * 8192u);
       const uint32_t wc_leader = mapa_u32(bar_wc_full, 0);
       for (int jb = 0; jb < p.fuse_njobs; ++jb)
-        for (int sl = 0; sl < 2; ++sl)
-          tma_load_2d_2sm(s_wc + (uint32_t)(jb * 2 + sl) * 4096u, jb ? &wmap1 : &wmap0, wc_leader, 0,
-                          (int)((sl * 8192u + rank * 4096u) >> 7));
+        for (uint32_t sp = 0; sp < 2u * kPl; ++sp)     // sp = slab * planes + plane
+          tma_load_2d_2sm(s_wc + ((uint32_t)jb * 2u * kPl + sp) * 4096u, jb ? &wmap1 : &wmap0, wc_leader, 0,
+                          (int)((sp * 8192u + rank * 4096u) >> 7));
     }
     __syncwarp();
     // rows (128 B) of one tap's weight block: the pair plan mixes 128-row (inner) and 64-row (outer) blocks
@@ -737,15 +786,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
       const CUtensorMap* bm = tl.job ? &bmap1 : &bmap0;
       for (int s = 0; s < p.nslab; ++s) {
         const int slab_row0 = (int)(((uint32_t)s * p.slab_bytes) >> 7);
-        static_for<TP::NT>([&](auto T) {
-          constexpr int t = decltype(T)::value;
+        static_for<NU>([&](auto U) {
+          constexpr int u = decltype(U)::value;
+          constexpr int t = SPLIT ? u / 2 : u, plane = SPLIT ? (u & 1) : 0, npl = SPLIT ? 2 : 1;
           constexpr bool outer = TP::outer(t);
-          constexpr int st = t % NST;
-          mbar_wait(bar_b_empty + 8 * st, slab_par ^ (uint32_t)((t / NST) & 1) ^ 1u);
+          constexpr int st = u % NST;
+          mbar_wait(bar_b_empty + 8 * st, slab_par ^ (uint32_t)((u / NST) & 1) ^ 1u);
           if (elect_one()) {
             // this CTA's half of the block: rows [rank * rows/2, (rank + 1) * rows/2) in 32-row (4 KB) boxes
             const int rows = KIND == TK_PAIR ? (outer ? 64 : 128) : tap_rows;
-            const int row0 = slab_row0 + (KIND == TK_PAIR ? TP::units_before(t) * 64 : t * tap_rows) + (int)rank * (rows >> 1);
+            const int row0 = slab_row0 + npl * (KIND == TK_PAIR ? TP::units_before(t) * 64 : t * tap_rows) + plane * rows +
+                             (int)rank * (rows >> 1);
             if (TC2_DBG(p, 2)) { if (leader) mbar_arrive(bar_b_full + 8 * st); }
             else {
               if (leader) mbar_expect_tx(bar_b_full + 8 * st, (uint32_t)rows << 7);
@@ -772,19 +823,33 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
       uint32_t prev_d = 0, y_uses = 0;
       bool wc_ready = false;
       auto service = [&](bool block) {
-        // issues the 1x1 MMAs of the next pending accumulator once its Y tile is complete in both CTAs
+        if (SPLIT) {
+          // split mode: hand-off prev_j covers the 64-channel slab (prev_j & 1) of the tile's accumulator
+          if (prev_left > 0 && (block || mbar_test(bar_y_full, y_uses & 1u))) {
+            const int n = fuse_service_split(prev_left, prev_j, prev_job, prev_d, y_uses, wc_ready, bar_y_full, bar_y_done,
+                                             bar_wc_full, s_y, s_wc, p.idesc_1x1, block);
+            prev_left -= n; prev_j += n; y_uses += (uint32_t)n;
+            wc_ready = true;
+          }
+          return;
+        }
+        // issues the 1x1 MMAs of the next pending hand-off once its Y tile is complete in both CTAs.  A hand-off is
+        // one accumulator (prev_j), or in split mode one 64-channel slab of it (accumulator prev_j >> 1, slab prev_j & 1:
+        // Y holds the hi and lo planes of that slab, and hi*hi + lo*hi + hi*lo accumulate into the 64 result columns).
         while (prev_left > 0) {
           if (block) mbar_wait(bar_y_full, y_uses & 1u);
           else if (!mbar_test(bar_y_full, y_uses & 1u)) return;
           if (!wc_ready) { mbar_wait(bar_wc_full, 0); wc_ready = true; }
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t d = prev_d + (uint32_t)(prev_j * 128);
+            {
+              const uint32_t d = prev_d + (uint32_t)(prev_j * 128);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t ad = desc_b | desc_addr(s_y + (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u);
-              const uint64_t bd = desc_b | desc_addr(s_wc + (uint32_t)(prev_job * 2 + (k >> 2)) * 4096u + (uint32_t)(k & 3) * 32u);
-              umma_f16_2sm(d, ad, bd, p.idesc_1x1, k ? 1u : 0u);
+              for (int k = 0; k < 8; ++k) {
+                const uint64_t ad = desc_b | desc_addr(s_y + (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u);
+                const uint64_t bd = desc_b | desc_addr(s_wc + (uint32_t)(prev_job * 2 + (k >> 2)) * 4096u + (uint32_t)(k & 3) * 32u);
+                umma_f16_2sm(d, ad, bd, p.idesc_1x1, k ? 1u : 0u);
+              }
             }
             umma_commit_2sm(bar_y_done);
           }
@@ -802,77 +867,127 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
       if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_all));
       int n_taps = 0;
 #endif
-      for (int item = cluster_id; item < total_items; item += nclusters, ++it) {
-        const Tile2 tl = decode_tile2<NACC>(p, item, 0);
-        const uint32_t outer_col = (uint32_t)p.job[tl.job].outer_col;
-        const int buf = it % p.nbuf;
-        const uint32_t aph = (uint32_t)(it / p.nbuf) & 1u;
+      // waits until the epilogue has released TMEM buffer `b` (use count -> parity)
+      auto acquire_acc = [&](int b, uint32_t par) {
 #ifdef CODON_TC_EXPERIMENT
-        if (prof) c_t = clock64();
+        const long long t_in = prof ? clock64() : 0;
 #endif
         if (FUSE) {
           // the epilogue of the tile that last used this TMEM buffer needs our 1x1 MMAs to finish: keep serving
-          while (!mbar_test(bar_acc_empty + 8 * buf, aph ^ 1)) service(false);
+          while (!mbar_test(bar_acc_empty + 8 * b, par)) service(false);
         } else {
-          mbar_wait(bar_acc_empty + 8 * buf, aph ^ 1);
+          mbar_wait(bar_acc_empty + 8 * b, par);
         }
 #ifdef CODON_TC_EXPERIMENT
-        if (prof) c_acc += clock64() - c_t;
+        if (prof) c_acc += clock64() - t_in;
 #endif
         tc_fence_after();
-        const uint32_t d_base = tmem_base + (uint32_t)buf * (uint32_t)NACC * n_cols;
+      };
+      int sbuf = 0;                 // split mode: next big buffer, its use parity, tiles issued so far
+      uint32_t sbuf_par = 0, tile_it = 0;
+      for (int item = cluster_id; item < total_items; item += nclusters) {
+        const Tile2 tl = decode_tile2<NACC>(p, item, 0);
+        const uint32_t outer_col = (uint32_t)p.job[tl.job].outer_col;
+        int buf = it % p.nbuf;
+        uint32_t d_base = 0;
+#ifdef CODON_TC_EXPERIMENT
+        if (prof) c_t = clock64();
+#endif
+        if (!SPLIT) {
+          acquire_acc(buf, ((uint32_t)(it / p.nbuf) & 1u) ^ 1u);
+          d_base = tmem_base + (uint32_t)buf * (uint32_t)NACC * n_cols;
+        }
         const int nacc_rt = tl.nacc;
         uint32_t acc0 = 0;                         // 0 only for the first K step of the tile
         for (int s = 0; s < p.nslab; ++s) {
           mbar_wait(bar_patch_full + 8 * ps, pph);
           const uint64_t a_base = desc_a | desc_addr(s_patch + ps * p.patch_stage);
+          const int ps_hi = ps;
+          uint64_t a_base_lo = 0;
+          if (SPLIT) {                             // the lo-plane patch of the slab sits in the next ring stage
+            if (++ps == p.npb) { ps = 0; pph ^= 1; }
+            mbar_wait(bar_patch_full + 8 * ps, pph);
+            a_base_lo = desc_a | desc_addr(s_patch + ps * p.patch_stage);
+          }
           const bool last_slab = s == p.nslab - 1;
           const uint32_t par_even = slab_par, par_odd = slab_par ^ 1u;
           // Straight-line code per tap: the A start address is the patch shifted by (dy rows, dx pixels), the ring
           // stage and its barriers are immediates.  The phase test of the NEXT tap's weights is issued before this
           // tap's MMAs so that its latency hides behind their issue.
           bool ready = mbar_test(bar_b_full, par_even);
-          static_for<TP::NT>([&](auto T) {
-            constexpr int t = decltype(T)::value;
+          static_for<NU>([&](auto U) {
+            constexpr int u = decltype(U)::value;
+            constexpr int t = SPLIT ? u / 2 : u, plane = SPLIT ? (u & 1) : 0;
             constexpr bool outer = TP::outer(t);
-            constexpr int st = t % NST;
+            constexpr int st = u % NST;
             constexpr uint32_t tap_off = ((uint32_t)TP::dy(t) * kPitch + (uint32_t)TP::dx(t) * 128u) >> 4;
+            // split mode: accumulation chunk = kTPC taps of this slab, in its own big / small accumulator pair
+            constexpr bool chunk_start = SPLIT && plane == 0 && (t % kTPC) == 0;
+            constexpr bool chunk_end = SPLIT && plane == 1 && (t % kTPC) == kTPC - 1;
+            if (chunk_start) {
+              buf = sbuf;
+              acquire_acc(buf, sbuf_par ^ 1u);
+              d_base = tmem_base + (uint32_t)buf * n_cols;
+              if (++sbuf == kSplitBufs) { sbuf = 0; sbuf_par ^= 1u; }
+              if (u == 0 && s == 0) {
+                // the tile's first small MMA overwrites the small accumulator: the previous tile's must have been read
+                if (FUSE) { while (!mbar_test(bar_small_empty, (tile_it & 1u) ^ 1u)) service(false); }
+                else mbar_wait(bar_small_empty, (tile_it & 1u) ^ 1u);
+                tc_fence_after();
+                ++tile_it;
+              }
+            }
             if (FUSE) service(false);
 #ifdef CODON_TC_EXPERIMENT
             if (prof) c_t = clock64();
 #endif
-            if (!ready) mbar_wait(bar_b_full + 8 * st, ((t / NST) & 1) ? par_odd : par_even);
+            if (!ready) mbar_wait(bar_b_full + 8 * st, ((u / NST) & 1) ? par_odd : par_even);
 #ifdef CODON_TC_EXPERIMENT
             if (prof) { c_wait += clock64() - c_t; ++n_taps; }
 #endif
-            if (t + 1 < TP::NT) ready = mbar_test(bar_b_full + 8 * ((t + 1) % NST), (((t + 1) / NST) & 1) ? par_odd : par_even);
+            if (u + 1 < NU) ready = mbar_test(bar_b_full + 8 * ((u + 1) % NST), (((u + 1) / NST) & 1) ? par_odd : par_even);
             tc_fence_after();
             const uint64_t bdesc = b_base + (uint64_t)(((uint32_t)st * kStageBytes) >> 4);
             const uint32_t idesc = outer ? idesc_half : idesc_full;
             const uint32_t d0 = d_base + (outer ? outer_col : 0u);
             if (elect_one()) {
+              // split: the hi weight block multiplies the hi and the lo activation patch, the lo block the hi patch
+              constexpr int ngroups = (SPLIT && plane == 0) ? 2 : 1;
 #pragma unroll
-              for (int j = 0; j < NACC; ++j) {
-                if (j < nacc_rt && !TC2_DBG(p, 8)) {
-                  // sub-tile j = (jx, jy): + jy*16 patch rows + jx*8 pixels
-                  const uint32_t sub_off = ((uint32_t)(j / G::NAX) * kTcSubH * kPitch + (uint32_t)(j % G::NAX) * kTcSubW * 128u) >> 4;
-                  const uint64_t adesc = a_base + (uint64_t)(tap_off + sub_off);
-                  const uint32_t d = d0 + (uint32_t)j * n_cols;
+              for (int g = 0; g < ngroups; ++g) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    // +32 B per K step inside the 128-B swizzled row == +2 in the 16-B address field
-                    const uint32_t acc = (t == 0 && k == 0) ? acc0 : 1u;
-                    if (OPERAND == TC_TF32) umma_tf32_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-                    else                    umma_f16_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                for (int j = 0; j < NACC; ++j) {
+                  if (j < nacc_rt && !TC2_DBG(p, 8)) {
+                    // sub-tile j = (jx, jy): + jy*16 patch rows + jx*8 pixels
+                    const uint32_t sub_off = ((uint32_t)(j / G::NAX) * kTcSubH * kPitch + (uint32_t)(j % G::NAX) * kTcSubW * 128u) >> 4;
+                    const uint64_t adesc = (g == 0 ? a_base : a_base_lo) + (uint64_t)(tap_off + sub_off);
+                    // split: hi*hi -> big accumulator, lo*hi and hi*lo -> small accumulator (n_cols further)
+                    const bool to_small = SPLIT && !(plane == 0 && g == 0);
+                    const uint32_t d = SPLIT ? (to_small ? tmem_base + (uint32_t)kSplitBufs * n_cols + (outer ? outer_col : 0u) : d0)
+                                             : d0 + (uint32_t)j * n_cols;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      // +32 B per K step inside the 128-B swizzled row == +2 in the 16-B address field
+                      // accumulate flag: 0 for the first MMA into an accumulator (split: per chunk, big and small)
+                      // (big: per chunk; small: per tile -- acc0 is 0 during the tile's first slab)
+                      const uint32_t acc = SPLIT ? (to_small ? ((u == 0 && k == 0) ? acc0 : 1u)
+                                                             : (((t % kTPC) == 0 && k == 0) ? 0u : 1u))
+                                                 : ((u == 0 && g == 0 && k == 0) ? acc0 : 1u);
+                      if (OPERAND == TC_TF32) umma_tf32_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                      else                    umma_f16_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                    }
                   }
                 }
               }
               umma_commit_2sm(bar_b_empty + 8 * st);
-              if (t == TP::NT - 1) {
-                umma_commit_2sm(bar_patch_empty + 8 * ps);
-                if (last_slab) umma_commit_2sm(bar_acc_full + 8 * buf);
+              if (u == NU - 1) {
+                umma_commit_2sm(bar_patch_empty + 8 * ps_hi);
+                if (SPLIT) umma_commit_2sm(bar_patch_empty + 8 * ps);
+                if (!SPLIT && last_slab) umma_commit_2sm(bar_acc_full + 8 * buf);
               }
+              if (chunk_end) umma_commit_2sm(bar_acc_full + 8 * buf);
             }
+            (void)chunk_end;
             __syncwarp();
           });
           acc0 = 1;
@@ -887,8 +1002,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
 #ifdef CODON_TC_EXPERIMENT
           if (prof) c_blk += clock64() - c_t;
 #endif
-          prev_left = tl.nacc; prev_j = 0; prev_job = tl.job; prev_d = d_base;
+          prev_left = SPLIT ? 2 : tl.nacc; prev_j = 0; prev_job = tl.job; prev_d = d_base;
         }
+        if (!SPLIT) ++it;
       }
       if (FUSE) service(true);
 #ifdef CODON_TC_EXPERIMENT
@@ -910,15 +1026,76 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     const int my = m / kTcSubW, mx = m % kTcSubW;
     const uint32_t acc_empty_leader = mapa_u32(bar_acc_empty, 0);
     const uint32_t y_full_leader = mapa_u32(bar_y_full, 0);
+    const uint32_t small_empty_leader = mapa_u32(bar_small_empty, 0);
     uint32_t y_uses = 0;                         // fused mode: Y hand-offs so far (phase of y_full / y_done)
+    int ep_sbuf = 0; uint32_t ep_sbuf_par = 0;   // split mode: next big buffer to promote and its use parity
     int it = 0;
     for (int item = cluster_id; item < total_items; item += nclusters, ++it) {
       const Tile2 tl = decode_tile2<NACC>(p, item, (int)rank);
       const TcJob& job = p.job[tl.job];
-      const int buf = it % p.nbuf;
-      mbar_wait(bar_acc_full + 8 * buf, (uint32_t)(it / p.nbuf) & 1u);
-      tc_fence_after();
-      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NACC * p.n_cols);
+      int buf = it % p.nbuf;
+      // split mode: this warp's 32-column groups (columns g * 64 + ehalf * 32 ...), promoted chunk by chunk into
+      // round-to-nearest fp32 running sums
+      constexpr int NG = SPLIT ? (KIND == TK_3X3 ? 1 : 2) : 1;
+      float tot[NG][32];
+      if (SPLIT) {
+        constexpr int NCH = TP::NT / kTPC;                       // chunks per slab
+        const uint32_t n_cols = (uint32_t)p.n_cols;
+        const int g_outer = job.outer_col >> 6;                  // pair plans: the group the 5x5-only taps feed
+        int& sbuf = ep_sbuf; uint32_t& sbuf_par = ep_sbuf_par;
+        for (int s = 0; s < p.nslab; ++s) {
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            // pair plans: a chunk made of border taps only carries the 5x5 half of the columns (a chunk starts with
+            // a border tap only if all of its taps are border taps: the issue order is centre-first)
+            const bool outer_only = KIND == TK_PAIR && ((TP::outer_chunk_mask(kTPC) >> c) & 1u);
+            buf = sbuf;
+            mbar_wait(bar_acc_full + 8 * buf, sbuf_par);
+            if (++sbuf == kSplitBufs) { sbuf = 0; sbuf_par ^= 1u; }
+            tc_fence_after();
+            const uint32_t lq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ehalf * 32u;
+            const uint32_t cb = lq + (uint32_t)buf * n_cols;
+            const bool last_chunk = (s == p.nslab - 1) && (c == NCH - 1);
+            uint32_t ra[NG][32];
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+              if (!outer_only || g == g_outer) tmem_ld32(cb + (uint32_t)g * 64u, ra[g]);      // warp-uniform predicate
+            tmem_ld_wait();
+            // the chunk is in registers: hand the buffer back before the additions (the fused kernel keeps the last
+            // one of a tile: the 1x1 result is computed into its first 64 columns)
+            if (!(FUSE && last_chunk)) {
+              tc_fence_before();
+              mbar_arrive_cluster(acc_empty_leader + 8 * buf);
+            }
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+              if (!outer_only || g == g_outer) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                  const float v = __uint_as_float(ra[g][e]);
+                  tot[g][e] = (c == 0 && s == 0) ? v : tot[g][e] + v;
+                }
+              }
+            }
+            if (last_chunk) {
+              // the tile's small accumulator (complete: the chunk's commit covers every earlier MMA)
+#pragma unroll
+              for (int g = 0; g < NG; ++g) tmem_ld32(lq + (uint32_t)kSplitBufs * n_cols + (uint32_t)g * 64u, ra[g]);
+              tmem_ld_wait();
+              tc_fence_before();
+              mbar_arrive_cluster(small_empty_leader);
+#pragma unroll
+              for (int g = 0; g < NG; ++g)
+#pragma unroll
+                for (int e = 0; e < 32; ++e) tot[g][e] += __uint_as_float(ra[g][e]);
+            }
+          }
+        }
+      } else {
+        mbar_wait(bar_acc_full + 8 * buf, (uint32_t)(it / p.nbuf) & 1u);
+        tc_fence_after();
+      }
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (SPLIT ? (uint32_t)buf * (uint32_t)p.n_cols : (uint32_t)(buf * NACC * p.n_cols));
       if (FUSE) {
         // accumulator j -> ReLU -> 16-bit -> Y (this warp: the 64 channels of slab `ehalf`), then the 1x1 result
         // (64 columns at the start of the same accumulator; this warp: 32 of them) -> (+ res2) -> out2
@@ -945,11 +1122,36 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           tc_fence_before();
           mbar_arrive_cluster_release(y_full_leader);
         };
+        // split mode: one 64-channel slab of accumulator j per hand-off; this warp converts 32 of its channels
+        // (columns slab * 64 + ehalf * 32 ...) of its 32 pixels: x = relu(acc) / scale -> hi = fp16(x), lo = fp16(x - hi)
+        // -> rows m of the hi tile (s_y) and of the lo tile (s_y + 16 KB), K-major SWIZZLE_128B
+        auto stage_y_split = [&](const float (&acc)[32]) {
+          const float ds = job.descale;
+          const uint32_t row = s_y + (uint32_t)m * 128u;
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2)
+              split_pair(fmaxf(acc[pc * 8 + 2 * t2], 0.f) * ds, fmaxf(acc[pc * 8 + 2 * t2 + 1], 0.f) * ds, h[t2], l[t2]);
+            const uint32_t off = (uint32_t)(((ehalf * 4 + pc) ^ (m & 7)) << 4);
+            st_shared_v4(row + off, h[0], h[1], h[2], h[3]);
+            st_shared_v4(row + 16384u + off, l[0], l[1], l[2], l[3]);
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive_cluster_release(y_full_leader);
+        };
         auto drain_d2 = [&](int j) {
           uint32_t r[32];
           if (TC2_DBG(p, 32)) return;
           tmem_ld32(lane_base + (uint32_t)(j * 128 + ehalf * 32), r);
           tmem_ld_wait();
+          if (SPLIT) {
+            const float ds2 = job.descale2;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * ds2);
+          }
           const int py = tl.y0 + (j / G::NAX) * kTcSubH + my, px = tl.x0 + (j % G::NAX) * kTcSubW + mx;
           if (tl.valid && (py < p.H) && (px < p.W) && !TC2_DBG(p, 1)) {
             const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
@@ -997,6 +1199,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           }
         };
         // Y is free here: the previous hand-off's y_done was awaited before its drain
+        if (SPLIT) {
+          // two hand-offs: the promoted sums of channel slab 0, then (once the 1x1 MMAs of slab 0 have read Y) slab 1
+          stage_y_split(tot[0]);
+          mbar_wait(bar_y_done, y_uses & 1u);
+          ++y_uses;
+          tc_fence_after();
+          stage_y_split(tot[NG - 1]);
+        } else {
         stage_y(0);
         for (int j = 1; j < tl.nacc; ++j) {
           mbar_wait(bar_y_done, y_uses & 1u);    // 1x1 of accumulator j-1 finished: Y is free, its result is in TMEM
@@ -1005,10 +1215,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           stage_y(j);
           drain_d2(j - 1);
         }
+        }
         mbar_wait(bar_y_done, y_uses & 1u);
         ++y_uses;
         tc_fence_after();
         drain_d2(tl.nacc - 1);
+      } else if (SPLIT) {
+        const int py = tl.y0 + my, px = tl.x0 + mx;
+        if (tl.valid && (py < p.H) && (px < p.W)) {
+          const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            uint32_t r[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(tot[g][e]);
+            store_chunk<OutT>(r, job, pix, g * 64 + ehalf * 32, p.relu != 0, false, job.descale);
+          }
+        }
       } else {
         const int cpa_sh = p.n_cols == 128 ? 2 : 1, nchunk = tl.nacc << cpa_sh;    // chunks per accumulator: 4 or 2
         auto issue = [&](int i, uint32_t (&r)[32]) { tmem_ld32(lane_base + (uint32_t)(i << 5), r); };
@@ -1017,7 +1240,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           const int py = tl.y0 + (j / G::NAX) * kTcSubH + my, px = tl.x0 + (j % G::NAX) * kTcSubW + mx;
           if (tl.valid && (py < p.H) && (px < p.W) && !TC2_DBG(p, 1)) {
             const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
-            store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32);
+            store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32, job.descale);
           }
         };
         // the two warps of a lane quarter take the even / odd chunks
@@ -1039,8 +1262,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         }
         }
       }
-      tc_fence_before();
-      mbar_arrive_cluster(acc_empty_leader + 8 * buf);
+      if (!SPLIT || FUSE) {        // (split, not fused: every chunk buffer was handed back right after its promotion)
+        tc_fence_before();
+        mbar_arrive_cluster(acc_empty_leader + 8 * buf);
+      }
     }
   }
 
@@ -1053,14 +1278,46 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   }
 }
 
+__device__ __noinline__ int fuse_service_split(int left, int j, int job, uint32_t d, uint32_t y_uses, bool wc_ready,
+                                               uint32_t bar_y_full, uint32_t bar_y_done, uint32_t bar_wc_full,
+                                               uint32_t s_y, uint32_t s_wc, uint32_t idesc_1x1, bool block) {
+  // Hand-off j covers the 64-channel slab (j & 1) of the tile's accumulator: Y holds that slab's hi plane (s_y) and
+  // lo plane (s_y + 16 KB); hi*hi + lo*hi + hi*lo accumulate into the 64 result columns at the start of the buffer.
+  const uint64_t desc_b = umma_desc_hi(1024);
+  int n = 0;
+  while (left > 0) {
+    if (block) mbar_wait(bar_y_full, y_uses & 1u);
+    else if (!mbar_test(bar_y_full, y_uses & 1u)) break;
+    if (!wc_ready) { mbar_wait(bar_wc_full, 0); wc_ready = true; }
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t slab = (uint32_t)(j & 1);
+      const uint32_t wc = s_wc + ((uint32_t)job * 4u + slab * 2u) * 4096u;      // [hi 4 KB][lo 4 KB] of this slab
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {            // 0: Y_hi * W_hi, 1: Y_lo * W_hi, 2: Y_hi * W_lo
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = desc_b | desc_addr(s_y + (g == 1 ? 16384u : 0u) + (uint32_t)k * 32u);
+          const uint64_t bd = desc_b | desc_addr(wc + (g == 2 ? 4096u : 0u) + (uint32_t)k * 32u);
+          umma_f16_2sm(d, ad, bd, idesc_1x1, (slab == 0 && g == 0 && k == 0) ? 0u : 1u);
+        }
+      }
+      umma_commit_2sm(bar_y_done);
+    }
+    __syncwarp();
+    ++y_uses; ++j; --left; ++n;
+  }
+  return n;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host helpers
 
 uint32_t make_idesc(int operand, int n, int m = 128) {
   // UMMA instruction descriptor: D = F32 (bits 4-5 = 1), A/B format (bits 7-9 / 10-12), both K-major,
   // N >> 3 at bit 17, M >> 4 at bit 24 (M = 128, or 256 for cta_group::2).
-  return (1u << 4) | ((uint32_t)operand << 7) | ((uint32_t)operand << 10) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);
+  const uint32_t fmt = (uint32_t)tc_umma_format(operand);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 inline uint16_t f32_to_bf16(float f) {
@@ -1082,11 +1339,21 @@ inline uint32_t f32_to_tf32(float f) {
 }
 
 // Writes element (row, k) of a K-major block with 128-B rows into its SWIZZLE_128B position.
-inline void put_elem(uint8_t* block, int row, int k, int esize, float v, int operand) {
+// TC_SPLIT16: `lo_block` is the lo-plane twin of the block; the value is scaled first (TcConvPlan::scale).
+inline void put_elem(uint8_t* block, int row, int k, int esize, float v, int operand, uint8_t* lo_block = nullptr,
+                     float scale = 1.f) {
   const int byte_in_row = k * esize;
   const int chunk = byte_in_row >> 4, within = byte_in_row & 15;
-  uint8_t* dst = block + (size_t)row * 128 + (size_t)((chunk ^ (row & 7)) << 4) + within;
+  const size_t off = (size_t)row * 128 + (size_t)((chunk ^ (row & 7)) << 4) + within;
+  uint8_t* dst = block + off;
   if (operand == TC_TF32) { const uint32_t u = f32_to_tf32(v); memcpy(dst, &u, 4); }
+  else if (operand == TC_SPLIT16) {
+    const float vs = v * scale;                       // exact: scale is a power of two
+    const __half h = __float2half_rn(vs);
+    const __half l = __float2half_rn(vs - __half2float(h));
+    memcpy(dst, &h, 2);
+    memcpy(lo_block + off, &l, 2);
+  }
   else { const uint16_t u = operand == TC_BF16 ? f32_to_bf16(v) : f32_to_f16(v); memcpy(dst, &u, 2); }
 }
 
@@ -1102,10 +1369,25 @@ void fill_orders(TcConvPlan& p, bool centre_first) {
 
 }  // namespace
 
-TcConvPlan tc_make_plan(int ks, int cin, int cout, int operand) {
+float tc_pick_scale(const float* w, size_t n, const float* w2, size_t n2) {
+  float mx = 0.f;
+  for (size_t i = 0; i < n; ++i) mx = std::fmax(mx, std::fabs(w[i]));
+  for (size_t i = 0; i < n2; ++i) mx = std::fmax(mx, std::fabs(w2[i]));
+  if (!(mx > 0.f) || !std::isfinite(mx)) return 1.f;
+  int e = 0;
+  std::frexp(mx, &e);                 // mx = f * 2^e, f in [0.5, 1)  ->  mx * 2^(11 - e) in [1024, 2048)
+  int k = 11 - e;
+  if (k > 60) k = 60;
+  if (k < -60) k = -60;
+  return std::ldexp(1.f, k);
+}
+
+TcConvPlan tc_make_plan(int ks, int cin, int cout, int operand, float scale) {
   TcConvPlan p;
   p.ks = ks; p.operand = operand;
   const int esize = operand == TC_TF32 ? 4 : 2;
+  p.split = operand == TC_SPLIT16 ? 1 : 0;
+  p.scale = p.split ? scale : 1.f;
   p.slab_elems = 128 / esize;
   p.nslab = cin / p.slab_elems;
   p.n_cols = cout;
@@ -1116,16 +1398,18 @@ TcConvPlan tc_make_plan(int ks, int cin, int cout, int operand) {
     for (int dyi = 0; dyi < p.ndy; ++dyi) {
       p.b_bytes[dxi][dyi] = (uint32_t)cout * 128u;
       p.b_off[dxi][dyi] = off;
-      off += p.b_bytes[dxi][dyi];
+      off += p.b_bytes[dxi][dyi] * (p.split ? 2u : 1u);
     }
   p.slab_bytes = off;
   return p;
 }
 
-TcConvPlan tc_make_pair_plan(int cin, int operand) {
+TcConvPlan tc_make_pair_plan(int cin, int operand, float scale) {
   TcConvPlan p;
   p.ks = 5; p.operand = operand;
   const int esize = operand == TC_TF32 ? 4 : 2;
+  p.split = operand == TC_SPLIT16 ? 1 : 0;
+  p.scale = p.split ? scale : 1.f;
   p.slab_elems = 128 / esize;
   p.nslab = cin / p.slab_elems;
   p.n_cols = 128;
@@ -1137,7 +1421,7 @@ TcConvPlan tc_make_pair_plan(int cin, int operand) {
       const bool inner = std::abs(p.dx_ord[dxi] - 2) <= 1 && std::abs(p.dy_ord[dyi] - 2) <= 1;
       p.b_bytes[dxi][dyi] = (inner ? 128u : 64u) * 128u;
       p.b_off[dxi][dyi] = off;
-      off += p.b_bytes[dxi][dyi];
+      off += p.b_bytes[dxi][dyi] * (p.split ? 2u : 1u);
     }
   p.slab_bytes = off;
   return p;
@@ -1151,11 +1435,12 @@ void tc_pack_weights(const TcConvPlan& p, const float* w, std::vector<uint8_t>& 
     for (int dxi = 0; dxi < p.ndx; ++dxi)
       for (int dyi = 0; dyi < p.ndy; ++dyi) {
         uint8_t* block = dst.data() + (size_t)s * p.slab_bytes + p.b_off[dxi][dyi];
+        uint8_t* lo = block + p.b_bytes[dxi][dyi];     // split plans only
         const int dx = p.dx_ord[dxi], dy = p.dy_ord[dyi];
         for (int n = 0; n < cout; ++n)
           for (int k = 0; k < p.slab_elems; ++k) {
             const int ci = s * p.slab_elems + k;
-            put_elem(block, n, k, esize, w[(((size_t)n * cin + ci) * ks + dy) * ks + dx], p.operand);
+            put_elem(block, n, k, esize, w[(((size_t)n * cin + ci) * ks + dy) * ks + dx], p.operand, lo, p.scale);
           }
       }
 }
@@ -1170,16 +1455,17 @@ void tc_pack_pair_weights(const TcConvPlan& p, const float* w3, const float* w5,
     for (int dxi = 0; dxi < 5; ++dxi)
       for (int dyi = 0; dyi < 5; ++dyi) {
         uint8_t* block = dst.data() + (size_t)s * p.slab_bytes + p.b_off[dxi][dyi];
+        uint8_t* lo = block + p.b_bytes[dxi][dyi];     // split plans only
         const int dx = p.dx_ord[dxi], dy = p.dy_ord[dyi];
         const bool inner = p.b_bytes[dxi][dyi] == 128u * 128u;
         for (int n = 0; n < 64; ++n)
           for (int k = 0; k < p.slab_elems; ++k) {
             const int ci = s * p.slab_elems + k;
             const float v5 = w5[(((size_t)n * cin + ci) * 5 + dy) * 5 + dx];
-            put_elem(block, inner ? row5 + n : n, k, esize, v5, p.operand);
+            put_elem(block, inner ? row5 + n : n, k, esize, v5, p.operand, lo, p.scale);
             if (inner) {
               const float v3 = w3[(((size_t)n * cin + ci) * 3 + (dy - 1)) * 3 + (dx - 1)];
-              put_elem(block, row3 + n, k, esize, v3, p.operand);
+              put_elem(block, row3 + n, k, esize, v3, p.operand, lo, p.scale);
             }
           }
       }
@@ -1199,7 +1485,9 @@ cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, i
     if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
     encode = reinterpret_cast<EncodeFn>(fn);
   }
-  const int es = act_bytes(act);
+  // split activations: the map sees the fp16 planes, a pixel of C containers = 2C fp16 ([64 hi | 64 lo] per slab)
+  const int es = act == ACT_SPLIT16 ? 2 : act_bytes(act);
+  if (act == ACT_SPLIT16) C *= 2;
   const CUtensorMapDataType dt = act == ACT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                : act == ACT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -1238,7 +1526,7 @@ cudaError_t tc_encode_bmap(CUtensorMap* map, const void* base, size_t bytes) {
 namespace {
 // shared geometry set-up; returns the dynamic shared memory the launch needs (0 if it does not fit)
 template <int NACC>
-size_t setup_geometry(TcKParams& kp, int b_stage_bytes_total) {
+size_t setup_geometry(TcKParams& kp, int b_stage_bytes_total, bool split = false) {
   using G = Geo<NACC>;
   kp.tiles_x = cdiv(kp.W, G::TW);
   kp.tiles_y = cdiv(kp.H, G::TH);
@@ -1249,9 +1537,11 @@ size_t setup_geometry(TcKParams& kp, int b_stage_bytes_total) {
   kp.patch_tx = (uint32_t)kp.pw * ph * 128u;
   kp.patch_stage = (kp.patch_tx + 1023u) & ~1023u;
   kp.nbuf = (2 * NACC * kp.n_cols <= 512) ? 2 : 1;
+  if (split) kp.nbuf = 2;        // two chunk buffers of [big n_cols][small n_cols] columns
   const size_t fixed = 1024 + kBarBytes + (size_t)b_stage_bytes_total;
   int npb = (int)((232448 - fixed) / kp.patch_stage);
   if (npb > kMaxNPB) npb = kMaxNPB;
+  if (split) npb &= ~1;          // hi / lo patches of a slab occupy two consecutive stages
   if (npb < 2) return 0;
   kp.npb = npb;
   return fixed + (size_t)npb * kp.patch_stage;
@@ -1268,9 +1558,10 @@ bool plan_matches_kind(const TcConvPlan& plan) {
     const int dxi = t / TP::KS, dyi = t % TP::KS;
     if (plan.dx_ord[dxi] != TP::dx(t) || plan.dy_ord[dyi] != TP::dy(t)) return false;
     const uint32_t bytes = (KIND == TK_PAIR ? (TP::outer(t) ? 64u : 128u) : (uint32_t)plan.n_cols) * 128u;
+    const uint32_t planes = plan.split ? 2u : 1u;
     if (plan.b_bytes[dxi][dyi] != bytes || plan.b_off[dxi][dyi] != off) return false;
-    if (KIND == TK_PAIR && off != (uint32_t)TP::units_before(t) * 8192u) return false;
-    off += bytes;
+    if (KIND == TK_PAIR && off != (uint32_t)TP::units_before(t) * 8192u * planes) return false;
+    off += bytes * planes;
   }
   return plan.slab_bytes == off;
 }
@@ -1290,8 +1581,9 @@ cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, con
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     sms_of_dev[dev].store(num_sms, std::memory_order_release);
   }
-  // fused mode adds the resident 1x1 weights (16 KB) and the Y staging tile (32 KB) behind the B ring
-  const size_t smem = setup_geometry<NACC>(kp, Taps<KIND>::NST * Taps<KIND>::kStageBytes + (FUSE ? 49152 : 0));
+  // fused mode adds the resident 1x1 weights (16 KB; split: 32 KB) and the Y staging tile (32 KB) behind the B ring
+  const size_t smem = setup_geometry<NACC>(kp, Taps<KIND>::NST * Taps<KIND>::kStageBytes + (FUSE ? (OPERAND == TC_SPLIT16 ? 65536 : 49152) : 0),
+                                           OPERAND == TC_SPLIT16);
   if (!smem) return cudaErrorInvalidConfiguration;
   if (kp.ks != Taps<KIND>::KS || (uint32_t)kp.n_cols * 64u > Taps<KIND>::kStageBytes) return cudaErrorInvalidValue;
   const int items = ((kp.tiles_per_job + 1) / 2) * kp.njobs;     // pair-tiles
@@ -1345,8 +1637,8 @@ cudaError_t launch_nacc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, TcKP
 
 int tc_selftest() {
   int bad = 0;
-  const int ops[3] = {TC_F16, TC_BF16, TC_TF32};
-  for (int oi = 0; oi < 3; ++oi) {
+  const int ops[4] = {TC_F16, TC_BF16, TC_TF32, TC_SPLIT16};
+  for (int oi = 0; oi < 4; ++oi) {
     const int op = ops[oi];
     if (!plan_matches_kind<TK_3X3>(tc_make_plan(3, 64, 64, op))) bad |= 1;
     if (!plan_matches_kind<TK_3X3>(tc_make_plan(3, 128, 64, op))) bad |= 1;
@@ -1355,10 +1647,12 @@ int tc_selftest() {
     if (!plan_matches_kind<TK_PAIR>(tc_make_pair_plan(64, op))) bad |= 4;
     if (plan_matches_kind<TK_5X5>(tc_make_pair_plan(64, op)) || plan_matches_kind<TK_PAIR>(tc_make_plan(5, 64, 128, op))) bad |= 8;
     // packing: element (n, ci, dy, dx) of an OIHW tensor must be found at row n, K index ci % slab of block (slab, tap)
-    const TcConvPlan p = tc_make_plan(3, 128, 64, op);
+    const TcConvPlan p = tc_make_plan(3, 128, 64, op, 8.f);
     const int es = op == TC_TF32 ? 4 : 2, cin = 128;
     std::vector<float> w((size_t)64 * cin * 9);
     for (size_t i = 0; i < w.size(); ++i) w[i] = (float)((int)(i % 251) - 125);      // exactly representable in every operand type
+    // split plans: 19 significant bits, only representable as hi + lo; the scale (8) must come back out
+    if (op == TC_SPLIT16) for (size_t i = 0; i < w.size(); ++i) w[i] += 1.f / 4096.f;
     std::vector<uint8_t> packed;
     tc_pack_weights(p, w.data(), packed);
     if (packed.size() != p.total_bytes()) { bad |= 16; continue; }
@@ -1376,6 +1670,10 @@ int tc_selftest() {
             uint16_t u; memcpy(&u, src, 2);
             if (op == TC_BF16) { uint32_t v = (uint32_t)u << 16; memcpy(&got, &v, 4); }
             else { __half h; memcpy(&h, &u, 2); got = __half2float(h); }
+            if (op == TC_SPLIT16) {
+              __half l; memcpy(&l, src + p.b_bytes[dxi][dyi], 2);
+              got = (got + __half2float(l)) / p.scale;
+            }
           }
           if (got != want) bad |= 32;
         }
@@ -1405,8 +1703,32 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, c
     if (dbg < 0) { const char* e = getenv("CODON_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     kp.debug = dbg;
   }
-  if (L.out_act != (plan.operand == TC_TF32 ? ACT_F32 : plan.operand == TC_BF16 ? ACT_BF16 : ACT_F16))
+  if (L.out_act != (plan.operand == TC_TF32 ? ACT_F32 : plan.operand == TC_BF16 ? ACT_BF16 : plan.operand == TC_SPLIT16 ? ACT_SPLIT16 : ACT_F16))
     return cudaErrorInvalidValue;   // activations are stored in the operand type
+  if (plan.operand == TC_SPLIT16) {
+    // split-fp16 operands: cluster kernel only; tile sizes whose two-plane patch ring fits shared memory
+    if (!L.two_cta || !L.bmap[0] || (L.njobs > 1 && !L.bmap[1])) return cudaErrorInvalidValue;
+    for (int i = 0; i < L.njobs; ++i) if (L.job[i].pool && !L.fuse) return cudaErrorInvalidValue;
+    const CUtensorMap& b0 = *L.bmap[0];
+    const CUtensorMap& b1 = *L.bmap[L.njobs > 1 ? 1 : 0];
+    if (L.fuse) {
+      if (plan.ks != 5 || plan.n_cols != 128 || plan.pair || L.nacc != 1 || !L.wmap[0] || (L.njobs > 1 && !L.wmap[1]) ||
+          L.y16_operand != TC_F16 || !plan_matches_kind<TK_5X5>(plan))
+        return cudaErrorInvalidValue;
+      kp.idesc_1x1 = make_idesc(TC_F16, 64, 256);
+      kp.fuse_njobs = L.njobs;
+      kp.pool_stride = L.pool_stride ? L.pool_stride : (unsigned long long)L.B * L.H * L.W;
+      kp.cells_x = cdiv(L.W, kTcSubW); kp.cells_y = cdiv(L.H, kTcSubH);
+      return launch_nacc2<1, TC_SPLIT16, true, TK_5X5>(tmap, tmapj1, b0, b1, *L.wmap[0], *L.wmap[L.njobs > 1 ? 1 : 0], kp, st);
+    }
+    if (plan.pair) {
+      if (L.nacc != 1 || !plan_matches_kind<TK_PAIR>(plan)) return cudaErrorInvalidValue;
+      return launch_nacc2<1, TC_SPLIT16, false, TK_PAIR>(tmap, tmapj1, b0, b1, b0, b1, kp, st);
+    }
+    if (plan.ks == 3 && L.nacc == 1 && plan_matches_kind<TK_3X3>(plan))
+      return launch_nacc2<1, TC_SPLIT16, false, TK_3X3>(tmap, tmapj1, b0, b1, b0, b1, kp, st);
+    return cudaErrorInvalidValue;
+  }
   for (int i = 0; i < L.njobs; ++i)
     if (L.job[i].pool && !L.fuse && (plan.n_cols != 64 || L.two_cta)) return cudaErrorInvalidValue;
   if (L.two_cta) {

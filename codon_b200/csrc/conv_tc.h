@@ -11,7 +11,11 @@ constexpr int kTcSubW = 8;            // an accumulator (128 GEMM rows) covers a
 constexpr int kTcSubH = 16;
 constexpr int kTcMaxTaps = 5;
 
-enum TcOperand : int { TC_F16 = 0, TC_BF16 = 1, TC_TF32 = 2 };   // == UMMA F16F32Format
+// TC_F16 / TC_BF16 / TC_TF32 == UMMA F16F32Format.  TC_SPLIT16 (F16X3 mode): every operand is carried as two fp16
+// planes hi = fp16(v), lo = fp16(v - hi) (~22 mantissa bits) and every K step issues hi*hi + lo*hi + hi*lo as three
+// kind::f16 MMAs into the same fp32 accumulator -- fp32-grade products at a third of the fp16 tensor rate.
+enum TcOperand : int { TC_F16 = 0, TC_BF16 = 1, TC_TF32 = 2, TC_SPLIT16 = 3 };
+inline int tc_umma_format(int operand) { return operand == TC_SPLIT16 ? TC_F16 : operand; }
 
 // Geometry of the packed B (weight) stream of one convolution: for every 128-byte input-channel
 // slab, for every tap in issue order, one K-major block of `rows` x 128 B, already in the
@@ -29,12 +33,21 @@ struct TcConvPlan {
   uint32_t b_off[kTcMaxTaps][kTcMaxTaps] = {};     // byte offset inside one slab group
   uint32_t slab_bytes = 0;
   int operand = TC_BF16;
+  // TC_SPLIT16: every tap's block is followed by its lo-plane twin (b_off = offset of the hi block, the lo block
+  // sits b_bytes later; slab_bytes covers both), and the weights are multiplied by `scale` (a power of two that
+  // moves them into the fp16 normal range so that the lo plane keeps its 11 bits) before the split; the kernel
+  // epilogue multiplies the accumulator by 1 / scale (TcJob::descale).
+  int split = 0;
+  float scale = 1.f;
   size_t total_bytes() const { return (size_t)slab_bytes * nslab; }
 };
 
+// Power-of-two scale that puts max|w| into [1024, 2048) (1 if all weights are zero).
+float tc_pick_scale(const float* w, size_t n, const float* w2 = nullptr, size_t n2 = 0);
+
 // Plans.  `cout`/`cin` in elements; the pair plan is 64 -> (64 | 64) with kernel sizes 3 and 5.
-TcConvPlan tc_make_plan(int ks, int cin, int cout, int operand);
-TcConvPlan tc_make_pair_plan(int cin, int operand);
+TcConvPlan tc_make_plan(int ks, int cin, int cout, int operand, float scale = 1.f);
+TcConvPlan tc_make_pair_plan(int cin, int operand, float scale = 1.f);
 
 // Pack OIHW fp32 weights into the plan's byte stream.  For a pair plan, w3 (3x3) and w5 (5x5)
 // are both [64][cin][k][k]; `three_first` puts the 3x3 result in columns 0..63 (depth branch,
@@ -51,6 +64,8 @@ struct TcJob {
   void* out;       int out_stride; int out_off;   // elements
   const void* res; int res_stride; int res_off;
   int outer_col;               // pair plans: accumulator column of the 5x5-only (outer) taps
+  float descale = 1.f;         // TC_SPLIT16: 1 / TcConvPlan::scale of this job's weights (applied to the accumulator)
+  float descale2 = 1.f;        // TC_SPLIT16, fused 1x1: 1 / scale of the 1x1 weights
   // fused 1x1 (TcLaunch::fuse): out2 = conv1x1(relu(this conv)) (+ res2), 64 channels of the activation type
   void* out2 = nullptr;       int out2_stride = 0; int out2_off = 0;
   const void* res2 = nullptr; int res2_stride = 0; int res2_off = 0;

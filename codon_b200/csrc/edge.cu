@@ -107,12 +107,12 @@ __global__ void __launch_bounds__(256) conv_last_kernel(const T* __restrict__ in
         // all kStrip + 2 loads of the row are issued back to back (clamped addresses, no branches between them);
         // out-of-image columns are zeroed afterwards
         const T* rowp = src + (ptrdiff_t)(dy - 1) * W * in_stride;
-        uint4 raw[kStrip + 2];
+        typename Act<T>::Raw raw[kStrip + 2];
 #pragma unroll
         for (int i = 0; i < kStrip + 2; ++i) {
           int xx = x0 + i - 1;
           xx = xx < 0 ? 0 : (xx >= W ? W - 1 : xx);
-          raw[i] = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)xx * in_stride));
+          raw[i] = Act<T>::ldg(rowp + (size_t)xx * in_stride);
         }
 #pragma unroll
         for (int i = 0; i < kStrip + 2; ++i) {
@@ -198,7 +198,7 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int stride, int o
   const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int p = p0 + r, c = c0 + threadIdx.x;
-    tile[r][threadIdx.x] = (p < HW && c < C) ? Act<T>::to_float(src[((size_t)b * HW + p) * stride + off + c]) : 0.f;
+    tile[r][threadIdx.x] = (p < HW && c < C) ? Act<T>::get(src + ((size_t)b * HW + p) * stride + off + c) : 0.f;
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -225,6 +225,8 @@ cudaError_t launch_conv_first(const float* x, const float* y, const float* w_d, 
     conv_first_kernel<float><<<grid_for(strips * 32, 256, kEdgeCtasPerSm), 256, 0, st>>>(x, y, w_d, w_c, (float*)out, B, H, W, rnd_tf32);
   else if (act == ACT_BF16)
     conv_first_kernel<__nv_bfloat16><<<grid_for(strips * 16, 256, kEdgeCtasPerSm), 256, 0, st>>>(x, y, w_d, w_c, (__nv_bfloat16*)out, B, H, W, 0);
+  else if (act == ACT_SPLIT16)
+    conv_first_kernel<split16><<<grid_for(strips * 16, 256, kEdgeCtasPerSm), 256, 0, st>>>(x, y, w_d, w_c, (split16*)out, B, H, W, 0);
   else
     conv_first_kernel<__half><<<grid_for(strips * 16, 256, kEdgeCtasPerSm), 256, 0, st>>>(x, y, w_d, w_c, (__half*)out, B, H, W, 0);
   return cudaGetLastError();
@@ -237,6 +239,8 @@ cudaError_t launch_conv_last(const void* in, int in_stride, int act, const float
     conv_last_kernel<float><<<grid_for(strips * 16, 256, kEdgeCtasPerSm), 256, 0, st>>>((const float*)in, in_stride, w, x, out, B, H, W);
   else if (act == ACT_BF16)
     conv_last_kernel<__nv_bfloat16><<<grid_for(strips * 8, 256, kEdgeCtasPerSm), 256, 0, st>>>((const __nv_bfloat16*)in, in_stride, w, x, out, B, H, W);
+  else if (act == ACT_SPLIT16)
+    conv_last_kernel<split16><<<grid_for(strips * 8, 256, kEdgeCtasPerSm), 256, 0, st>>>((const split16*)in, in_stride, w, x, out, B, H, W);
   else
     conv_last_kernel<__half><<<grid_for(strips * 8, 256, kEdgeCtasPerSm), 256, 0, st>>>((const __half*)in, in_stride, w, x, out, B, H, W);
   return cudaGetLastError();
@@ -265,6 +269,7 @@ cudaError_t launch_nhwc_to_nchw_f32(const void* src, int act, int stride, int of
   dim3 grid(cdiv(HW, 32), cdiv(C, 32), B), block(32, 8);
   if (act == ACT_F32) nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>((const float*)src, stride, off, C, HW, dst);
   else if (act == ACT_BF16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)src, stride, off, C, HW, dst);
+  else if (act == ACT_SPLIT16) nhwc_to_nchw_kernel<split16><<<grid, block, 0, st>>>((const split16*)src, stride, off, C, HW, dst);
   else nhwc_to_nchw_kernel<__half><<<grid, block, 0, st>>>((const __half*)src, stride, off, C, HW, dst);
   return cudaGetLastError();
 }

@@ -16,7 +16,7 @@ import torch
 
 from . import build as _build
 
-MODES = {"fp32": 0, "bf16": 1, "fp16": 2, "tf32": 3}
+MODES = {"fp32": 0, "bf16": 1, "fp16": 2, "tf32": 3, "f16x3": 4}
 _IO_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
 # every symbol include/codon_b200.h declares (tests/test_abi.py checks the list against the header)

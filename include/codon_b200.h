@@ -43,13 +43,19 @@ typedef enum codon_status {
  *   FP16 : as BF16 with fp16 operands (what the reference runs on GPU: model.half(),
  *          CODON_X4/test.py:52).
  *   TF32 : fp32 NHWC activations, tcgen05 kind::tf32, fp32 accumulation.
+ *   F16X3: fp32-accurate tensor-core mode.  Activations and weights are carried as two fp16 planes
+ *          (hi = fp16(v), lo = fp16(v - hi): ~22 mantissa bits; weights pre-scaled by a power of two
+ *          into the fp16 normal range) and every K step issues hi*hi + lo*hi + hi*lo as three
+ *          tcgen05 kind::f16 MMAs into one fp32 TMEM accumulator.  Same 4 bytes per activation
+ *          element as TF32, one third of the FP16 tensor rate, products as accurate as fp32.
  * In every mode the depth input, the global residual add and the output stay fp32, and the
  * CAC statistics / gates are computed in fp32. */
 typedef enum codon_mode {
   CODON_MODE_FP32 = 0,
   CODON_MODE_BF16 = 1,
   CODON_MODE_FP16 = 2,
-  CODON_MODE_TF32 = 3
+  CODON_MODE_TF32 = 3,
+  CODON_MODE_F16X3 = 4
 } codon_mode;
 
 /* dtype of the frames passed to codon_forward */
