@@ -34,13 +34,37 @@ class _StubModule(nn.Module):
             self.__dict__.setdefault(k, collections.OrderedDict())
 
 
+# Modules a checkpoint may import from while being unpickled: torch's own tensor / parameter / container machinery
+# and the numpy reconstructors torch.save can emit.  Every other class the pickle names -- the training-time model
+# classes (``base_net_withoutBN...``, ``CODON_x4.CODONNet``, ``model.CODONet...``), and anything an attacker put there --
+# is mapped to a stub nn.Module WITHOUT being imported, so that loading never executes code from the working
+# directory or from arbitrary installed packages.  (A whole-module .pth is still a pickle: only load files you trust.)
+_ALLOWED_PREFIXES = ("torch", "collections", "numpy", "_codecs", "builtins", "copyreg")
+_ALLOWED_BUILTINS = {"set", "frozenset", "dict", "list", "tuple", "int", "float", "bool", "str", "bytes", "bytearray",
+                     "complex", "slice", "range", "object", "getattr"}
+
+
+def _import_allowed(module: str, name: str) -> bool:
+    root = module.split(".", 1)[0]
+    if root not in _ALLOWED_PREFIXES:
+        return False
+    if root == "builtins":
+        return name in _ALLOWED_BUILTINS and name != "getattr"
+    return True
+
+
 class _LenientUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
-        try:
-            mod = importlib.import_module(module)
-            return getattr(mod, name)
-        except Exception:
-            return type(name, (_StubModule,), {"__module__": module})
+        if _import_allowed(module, name):
+            try:
+                mod = importlib.import_module(module)
+                obj = mod
+                for part in name.split("."):
+                    obj = getattr(obj, part)
+                return obj
+            except Exception:
+                pass
+        return type(name.rsplit(".", 1)[-1], (_StubModule,), {"__module__": module})
 
 
 class _LenientPickle:
@@ -99,3 +123,56 @@ def load_checkpoint(path: str) -> Tuple[Dict[str, torch.Tensor], dict]:
 def infer_scale(sd: Dict[str, torch.Tensor]) -> str:
     """'x4/x8' checkpoints carry attention_c5 / attention_s5 (CODON_x4.py:64-65); x16 ones do not."""
     return "x4/x8" if any(k.startswith("attention_c5.") for k in sd) else "x16"
+
+
+# ---- flat weight file: the C-host route (SURVEY.md 8f row 3) --------------------------------------------------------
+_FLAT_MAGIC = b"CODONW1\0"
+
+
+def export_flat(sd: Dict[str, torch.Tensor], path: str) -> int:
+    """Writes a state_dict as the flat little-endian file ``codon_load_weights_file`` (include/codon_b200.h) reads:
+    ``"CODONW1\\0" | uint32 n | n x { uint16 name_len | name | uint8 ndim | ndim x int64 dims | float32 data }``.
+    A leading ``module.`` is stripped.  Returns the number of tensors written."""
+    import struct
+    items = []
+    for k, v in sd.items():
+        while k.startswith("module."):
+            k = k[len("module."):]
+        items.append((k, v.detach().to("cpu", torch.float32).contiguous()))
+    with open(path, "wb") as f:
+        f.write(_FLAT_MAGIC)
+        f.write(struct.pack("<I", len(items)))
+        for k, t in items:
+            name = k.encode("utf-8")
+            if not (0 < len(name) < 256) or not (1 <= t.dim() <= 4):
+                raise ValueError(f"cannot export {k!r} with shape {tuple(t.shape)}")
+            f.write(struct.pack("<H", len(name)))
+            f.write(name)
+            f.write(struct.pack("<B", t.dim()))
+            f.write(struct.pack(f"<{t.dim()}q", *t.shape))
+            f.write(t.numpy().astype("<f4", copy=False).tobytes())
+    return len(items)
+
+
+def load_flat(path: str) -> Dict[str, torch.Tensor]:
+    """Reads a file written by ``export_flat`` back into a state_dict (the Python twin of the C loader)."""
+    import struct
+    import numpy as np
+    out: Dict[str, torch.Tensor] = {}
+    with open(path, "rb") as f:
+        if f.read(8) != _FLAT_MAGIC:
+            raise ValueError(f"{path} is not a CODONW1 weight file")
+        (n,) = struct.unpack("<I", f.read(4))
+        for _ in range(n):
+            (ln,) = struct.unpack("<H", f.read(2))
+            name = f.read(ln).decode("utf-8")
+            (nd,) = struct.unpack("<B", f.read(1))
+            dims = struct.unpack(f"<{nd}q", f.read(8 * nd))
+            cnt = 1
+            for d in dims:
+                cnt *= d
+            buf = f.read(4 * cnt)
+            if len(buf) != 4 * cnt:
+                raise ValueError(f"{path}: truncated data of {name!r}")
+            out[name] = torch.from_numpy(np.frombuffer(buf, dtype="<f4").reshape(dims).copy())
+    return out

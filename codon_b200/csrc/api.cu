@@ -77,6 +77,13 @@ struct codon_ctx {
   std::string err;
   int launches = 0;
   std::vector<void*> dev_allocs;
+  // Weight uploads of the previous finalize, in upload order: a re-finalize (load_state_dict after a forward) copies
+  // into the same allocations when the sizes match, so device pointers and tensor maps baked into a captured CUDA
+  // graph stay valid.  `generation` counts successful finalizes (GraphedForward re-captures when it moves: the
+  // kernel parameters of a graph also hold per-layer weight scales).
+  std::vector<size_t> alloc_bytes;
+  size_t upload_cursor = 0;
+  unsigned long long generation = 0;
 
   // fp32 direct-conv weights [T][Cin][Cout]
   std::map<std::string, float*> w_direct;
@@ -192,10 +199,21 @@ Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W, int part_chunks 
 
 template <typename T>
 int upload(codon_ctx* ctx, const std::vector<T>& host, T** dev) {
+  const size_t bytes = host.size() * sizeof(T);
   void* p = nullptr;
-  CU_TRY(ctx, cudaMalloc(&p, host.size() * sizeof(T)));
-  ctx->dev_allocs.push_back(p);
-  CU_TRY(ctx, cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  if (ctx->upload_cursor < ctx->dev_allocs.size() && ctx->alloc_bytes[ctx->upload_cursor] == bytes) {
+    p = ctx->dev_allocs[ctx->upload_cursor];          // same upload sequence as last time: reuse in place
+  } else {
+    // first finalize, or the sequence changed: drop this and every later allocation of the old sequence
+    for (size_t i = ctx->upload_cursor; i < ctx->dev_allocs.size(); ++i) cudaFree(ctx->dev_allocs[i]);
+    ctx->dev_allocs.resize(ctx->upload_cursor);
+    ctx->alloc_bytes.resize(ctx->upload_cursor);
+    CU_TRY(ctx, cudaMalloc(&p, bytes));
+    ctx->dev_allocs.push_back(p);
+    ctx->alloc_bytes.push_back(bytes);
+  }
+  ctx->upload_cursor++;
+  CU_TRY(ctx, cudaMemcpy(p, host.data(), bytes, cudaMemcpyHostToDevice));
   *dev = static_cast<T*>(p);
   return CODON_OK;
 }
@@ -827,9 +845,10 @@ int codon_finalize_weights(codon_ctx* ctx) {
       snprintf(key, sizeof(key), "attention_%s", buf);
       if (!find_w(ctx, key)) return fail(ctx, CODON_ERR_STATE, "codon_finalize_weights: missing parameter '%s'", key);
     }
-  // drop earlier uploads
-  for (void* p : ctx->dev_allocs) cudaFree(p);
-  ctx->dev_allocs.clear(); ctx->w_direct.clear(); ctx->w_tc.clear(); ctx->tmaps.clear();
+  // earlier uploads are overwritten in place (same sizes in the same order); nothing in flight may read them
+  CU_TRY(ctx, cudaDeviceSynchronize());
+  ctx->upload_cursor = 0;
+  ctx->w_direct.clear(); ctx->w_tc.clear();
 
   int rc;
   auto W = [&](const char* n) -> const HostTensor& { return *find_w(ctx, std::string(n) + ".weight"); };
@@ -901,8 +920,50 @@ int codon_finalize_weights(codon_ctx* ctx) {
       ctx->w_tc[p.name] = l;
     }
   }
+  // allocations of a longer previous sequence (never happens for one mode; kept for safety)
+  for (size_t i = ctx->upload_cursor; i < ctx->dev_allocs.size(); ++i) cudaFree(ctx->dev_allocs[i]);
+  ctx->dev_allocs.resize(ctx->upload_cursor);
+  ctx->alloc_bytes.resize(ctx->upload_cursor);
   ctx->finalized = true;
+  ctx->generation++;
   return CODON_OK;
+}
+
+unsigned long long codon_weights_generation(const codon_ctx* ctx) { return ctx ? ctx->generation : 0; }
+
+// Flat weight file (codon_b200.checkpoint.export_flat): "CODONW1\0", uint32 count, then per tensor
+// uint16 name length, name bytes, uint8 ndim, ndim x int64 dims, prod(dims) x float32 -- little endian, no padding.
+int codon_load_weights_file(codon_ctx* ctx, const char* path) {
+  if (!ctx || !path) return fail(ctx, CODON_ERR_ARG, "codon_load_weights_file: bad argument");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(ctx, CODON_ERR_ARG, "codon_load_weights_file: cannot open '%s'", path);
+  struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+  char magic[8];
+  uint32_t count = 0;
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "CODONW1\0", 8) != 0 || fread(&count, 4, 1, f) != 1 || count > 4096)
+    return fail(ctx, CODON_ERR_ARG, "codon_load_weights_file: '%s' is not a CODONW1 weight file", path);
+  std::vector<float> data;
+  for (uint32_t i = 0; i < count; ++i) {
+    uint16_t nlen = 0;
+    uint8_t ndim = 0;
+    char name[256];
+    int64_t dims[4];
+    if (fread(&nlen, 2, 1, f) != 1 || nlen == 0 || nlen >= sizeof(name) || fread(name, 1, nlen, f) != nlen ||
+        fread(&ndim, 1, 1, f) != 1 || ndim < 1 || ndim > 4 || fread(dims, 8, ndim, f) != ndim)
+      return fail(ctx, CODON_ERR_ARG, "codon_load_weights_file: truncated or malformed entry %u", i);
+    name[nlen] = 0;
+    size_t n = 1;
+    for (int d = 0; d < ndim; ++d) {
+      if (dims[d] < 1 || dims[d] > (1 << 20)) return fail(ctx, CODON_ERR_ARG, "codon_load_weights_file: bad shape for '%s'", name);
+      n *= (size_t)dims[d];
+    }
+    if (n > ((size_t)1 << 26)) return fail(ctx, CODON_ERR_ARG, "codon_load_weights_file: '%s' is too large", name);
+    data.resize(n);
+    if (fread(data.data(), 4, n, f) != n) return fail(ctx, CODON_ERR_ARG, "codon_load_weights_file: truncated data of '%s'", name);
+    int rc = codon_set_weight(ctx, name, data.data(), dims, ndim);
+    if (rc) return rc;
+  }
+  return codon_finalize_weights(ctx);
 }
 
 size_t codon_workspace_bytes(const codon_ctx* ctx, int B, int H, int W) {

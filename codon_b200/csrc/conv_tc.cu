@@ -92,12 +92,19 @@ template <int NACC> struct Geo {
 // straight-line code per tap (descriptor offsets and byte counts are immediates).  Must match fill_orders() /
 // tc_make_plan() / tc_make_pair_plan() below (checked on the host before every launch).
 enum TcKind : int { TK_3X3 = 0, TK_5X5 = 1, TK_PAIR = 2 };
-// split-fp16 mode: taps per accumulation chunk (see conv_tc2_kernel); must divide 9 resp. 25
+// split-fp16 mode: taps per accumulation chunk (see conv_tc2_kernel); must divide 9 resp. 25.  Measured on B200
+// (profiles/r02_split_chunking.txt): one tap per chunk gives the smallest error (mean |err| 7.2e-8 vs the fp64
+// reference, fp32 FFMA mode: 3.6e-8) at 20 MP/s; one column of taps per chunk 1.05e-7 at 25 MP/s, and both reproduce
+// the reference's RMSE / SSIM to three decimals on all 30 bundled images -- the faster one is the default.
 #ifndef CODON_SPLIT_TPC_3X3
-#define CODON_SPLIT_TPC_3X3 1
+#define CODON_SPLIT_TPC_3X3 3
 #endif
 #ifndef CODON_SPLIT_TPC_5X5
-#define CODON_SPLIT_TPC_5X5 1
+#define CODON_SPLIT_TPC_5X5 5
+#endif
+// split-fp16 mode: on the hi weight block, alternate the big / small accumulators K step by K step (+1 %)
+#ifndef CODON_SPLIT_INTERLEAVE
+#define CODON_SPLIT_INTERLEAVE 1
 #endif
 template <int KIND> struct Taps {
   static constexpr int KS = KIND == TK_3X3 ? 3 : 5;
@@ -720,8 +727,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap1) : "memory");
     for (int i = 0; i < p.npb; ++i) { mbar_init(bar_patch_full + 8 * i, 1); mbar_init(bar_patch_empty + 8 * i, 1); }
     for (int i = 0; i < NST; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 512); }
-    mbar_init(bar_y_full, 512); mbar_init(bar_y_done, 1); mbar_init(bar_wc_full, 1); mbar_init(bar_small_empty, 512);
+    // accumulator hand-backs: every epilogue thread of both CTAs arrives (512); split mode hands a buffer back per
+    // accumulation chunk, so there one lane per epilogue warp arrives (2 x 8) -- 512 serialised remote arrivals per
+    // chunk were most of the promotion's turn-around time
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, SPLIT ? 16 : 512); }
+    mbar_init(bar_y_full, 512); mbar_init(bar_y_done, 1); mbar_init(bar_wc_full, 1); mbar_init(bar_small_empty, 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWarpMma) {
@@ -953,6 +963,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             if (elect_one()) {
               // split: the hi weight block multiplies the hi and the lo activation patch, the lo block the hi patch
               constexpr int ngroups = (SPLIT && plane == 0) ? 2 : 1;
+#if CODON_SPLIT_INTERLEAVE
+              if (SPLIT && plane == 0) {
+                const uint32_t d_small = tmem_base + (uint32_t)kSplitBufs * n_cols + (outer ? outer_col : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_f16_2sm(d0, a_base + (uint64_t)tap_off + 2 * k, bdesc + 2 * k, idesc, ((t % kTPC) == 0 && k == 0) ? 0u : 1u);
+                  umma_f16_2sm(d_small, a_base_lo + (uint64_t)tap_off + 2 * k, bdesc + 2 * k, idesc, (u == 0 && k == 0) ? acc0 : 1u);
+                }
+              } else
+#endif
 #pragma unroll
               for (int g = 0; g < ngroups; ++g) {
 #pragma unroll
@@ -1059,17 +1079,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             uint32_t ra[NG][32];
 #pragma unroll
             for (int g = 0; g < NG; ++g)
-              if (!outer_only || g == g_outer) tmem_ld32(cb + (uint32_t)g * 64u, ra[g]);      // warp-uniform predicate
+              if ((!outer_only || g == g_outer) && !TC2_DBG(p, 32)) tmem_ld32(cb + (uint32_t)g * 64u, ra[g]);      // warp-uniform predicate
             tmem_ld_wait();
             // the chunk is in registers: hand the buffer back before the additions (the fused kernel keeps the last
             // one of a tile: the 1x1 result is computed into its first 64 columns)
             if (!(FUSE && last_chunk)) {
               tc_fence_before();
-              mbar_arrive_cluster(acc_empty_leader + 8 * buf);
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8 * buf);
             }
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
-              if (!outer_only || g == g_outer) {
+              if ((!outer_only || g == g_outer) && !TC2_DBG(p, 32)) {
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                   const float v = __uint_as_float(ra[g][e]);
@@ -1083,7 +1104,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
               for (int g = 0; g < NG; ++g) tmem_ld32(lq + (uint32_t)kSplitBufs * n_cols + (uint32_t)g * 64u, ra[g]);
               tmem_ld_wait();
               tc_fence_before();
-              mbar_arrive_cluster(small_empty_leader);
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(small_empty_leader);
 #pragma unroll
               for (int g = 0; g < NG; ++g)
 #pragma unroll
@@ -1262,7 +1284,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         }
         }
       }
-      if (!SPLIT || FUSE) {        // (split, not fused: every chunk buffer was handed back right after its promotion)
+      if (SPLIT) {
+        if (FUSE) {                // (split, not fused: every chunk buffer was handed back right after its promotion)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8 * buf);
+        }
+      } else {
         tc_fence_before();
         mbar_arrive_cluster(acc_empty_leader + 8 * buf);
       }

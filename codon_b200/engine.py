@@ -22,7 +22,7 @@ _IO_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 # every symbol include/codon_b200.h declares (tests/test_abi.py checks the list against the header)
 ABI_SYMBOLS = [
     "codon_create", "codon_destroy", "codon_last_error", "codon_version", "codon_selftest", "codon_set_weight",
-    "codon_finalize_weights", "codon_workspace_bytes", "codon_forward", "codon_forward_host",
+    "codon_finalize_weights", "codon_weights_generation", "codon_load_weights_file", "codon_workspace_bytes", "codon_forward", "codon_forward_host",
     "codon_forward_host_submit", "codon_forward_host_wait",
     "codon_last_launch_count", "codon_debug_tap", "codon_profile_enable", "codon_profile_read",
     "codon_profile_reset", "codon_profile_category_name", "codon_cac_channel", "codon_cac_spatial",
@@ -68,6 +68,9 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         lib.codon_finalize_weights.argtypes = [vp]
         lib.codon_workspace_bytes.argtypes = [vp, ip, ip, ip]
         lib.codon_workspace_bytes.restype = c.c_size_t
+        lib.codon_weights_generation.argtypes = [vp]
+        lib.codon_load_weights_file.argtypes = [vp, c.c_char_p]
+        lib.codon_weights_generation.restype = c.c_ulonglong
         lib.codon_forward.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, vp, c.c_size_t, vp]
         lib.codon_forward_host.argtypes = [vp, vp, vp, vp, ip, ip, ip]
         lib.codon_forward_host_submit.argtypes = [vp, vp, vp, vp, ip, ip, ip]
@@ -102,6 +105,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         for name in ABI_SYMBOLS:
             fn = getattr(lib, name)
             if name not in ("codon_destroy", "codon_last_error", "codon_version", "codon_selftest", "codon_workspace_bytes",
+                            "codon_weights_generation",
                             "codon_profile_category_name", "codon_group_destroy", "codon_group_last_error",
                             "codon_group_last_ms"):
                 fn.restype = c.c_int
@@ -167,6 +171,15 @@ class Engine:
             check(self.lib.codon_set_weight(self._ctx, name.encode(), ctypes.cast(a.data_ptr(), ctypes.POINTER(ctypes.c_float)),
                                             shape, a.dim()), self._ctx)
         check(self.lib.codon_finalize_weights(self._ctx), self._ctx)
+
+    def load_weights_file(self, path: str) -> None:
+        """Loads a flat weight file written by ``codon_b200.checkpoint.export_flat`` (the C-host route)."""
+        check(self.lib.codon_load_weights_file(self._ctx, os.fsencode(path)), self._ctx)
+
+    @property
+    def weights_generation(self) -> int:
+        """Bumped by every load_state_dict; captured graphs re-capture when it moves."""
+        return int(self.lib.codon_weights_generation(self._ctx))
 
     # ---- forward ---------------------------------------------------------------------------------
     def workspace_bytes(self, B: int, H: int, W: int) -> int:
@@ -316,6 +329,14 @@ class GraphedForward:
         self.x = torch.zeros(B, 1, H, W, dtype=dtype, device=dev)
         self.y = torch.zeros(B, 1, H, W, dtype=dtype, device=dev)
         self.out = torch.empty(B, 1, H, W, dtype=dtype, device=dev)
+        self._capture()
+
+    def _capture(self) -> None:
+        """(Re-)captures the forward.  The graph bakes in device pointers (weights, workspace) and per-layer constants
+        derived from the weights; ``Engine.load_state_dict`` keeps the pointers valid (in-place re-upload) and bumps
+        ``weights_generation``, which ``replay`` checks."""
+        eng, dev = self.eng, self.eng.device
+        self.generation = eng.weights_generation
         eng.profile_enable(False)
         with torch.cuda.device(dev):
             side = torch.cuda.Stream(device=dev)
@@ -332,11 +353,13 @@ class GraphedForward:
     def __call__(self, depth: torch.Tensor, guide: torch.Tensor) -> torch.Tensor:
         self.x.copy_(depth.reshape(self.x.shape))
         self.y.copy_(guide.reshape(self.y.shape))
-        self.graph.replay()
-        return self.out
+        return self.replay()
 
     def replay(self) -> torch.Tensor:
-        """Replays on the data already in ``self.x`` / ``self.y``."""
+        """Replays on the data already in ``self.x`` / ``self.y`` (after re-capturing if the engine's weights were
+        reloaded since the capture)."""
+        if self.eng.weights_generation != self.generation:
+            self._capture()
         self.graph.replay()
         return self.out
 

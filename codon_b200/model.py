@@ -15,6 +15,7 @@ Arithmetic mode follows the parameter dtype, as in the reference (test.py:52 ``.
 """
 from __future__ import annotations
 
+import threading
 from math import sqrt
 from typing import Dict, Optional, Tuple
 
@@ -61,6 +62,9 @@ class CODONNetBase(nn.Module):
             self.attention_s5 = CAC_spatial()
         self._mode_override: Optional[str] = None
         self._engines: Dict[Tuple[int, str], Tuple[_eng.Engine, tuple]] = {}
+        self._engine_lock = threading.Lock()          # DataParallel replicas share _engines across threads
+        self._wver = 0
+        self._plist = None
 
     # ---- engine management --------------------------------------------------------------------
     def set_mode(self, mode: Optional[str]) -> "CODONNetBase":
@@ -75,8 +79,37 @@ class CODONNetBase(nn.Module):
             return self._mode_override
         return _DTYPE_MODE.get(self.input.weight.dtype, "fp32")
 
+    # Weight changes are tracked by a version counter that every nn.Module-level mutation bumps (load_state_dict, and
+    # _apply = .cuda() / .half() / .to() / .float()), plus the autograd version counters of the parameters (in-place
+    # ops through the Parameter itself: p.copy_(), p.mul_()).  In-place edits through ``.data`` (p.data.normal_(), the
+    # reference's own init idiom, CODON_x4.py:53) bump neither: call ``refresh_weights()`` after such an edit.
+    def load_state_dict(self, *args, **kwargs):
+        res = super().load_state_dict(*args, **kwargs)
+        self._wver += 1
+        return res
+
+    def _apply(self, fn, *args, **kwargs):
+        res = super()._apply(fn, *args, **kwargs)
+        self._wver += 1
+        self._plist = None
+        return res
+
+    def refresh_weights(self) -> "CODONNetBase":
+        """Forces the engines to re-read the parameters on the next forward (needed only after in-place edits through
+        ``param.data``, which PyTorch does not version)."""
+        self._wver += 1
+        return self
+
+    invalidate = refresh_weights
+
     def _weights_key(self) -> tuple:
-        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
+        if getattr(self, "_is_replica", False):
+            # torch.nn.DataParallel replica: its parameters are fresh broadcast copies on every forward; the master's
+            # counter (copied at replication time) is the only meaningful version
+            return (self._wver, None)
+        if self._plist is None:
+            self._plist = list(self.parameters())
+        return (self._wver, tuple((p.data_ptr(), p._version) for p in self._plist))
 
     def engine(self, device: torch.device) -> _eng.Engine:
         """The (cached) engine for this device/mode, with the current parameter values uploaded."""
@@ -84,11 +117,15 @@ class CODONNetBase(nn.Module):
         key = (device.index if device.index is not None else torch.cuda.current_device(), mode)
         wkey = self._weights_key()
         hit = self._engines.get(key)
-        if hit is not None and hit[1] == wkey:
+        if hit is not None and hit[1][0] == wkey[0] and (wkey[1] is None or hit[1][1] is None or hit[1][1] == wkey[1]):
             return hit[0]
-        eng = hit[0] if hit is not None else _eng.Engine(self.SCALE, mode, key[0])
-        eng.load_state_dict({k: v for k, v in self.state_dict().items()})
-        self._engines[key] = (eng, wkey)
+        with self._engine_lock:
+            hit = self._engines.get(key)
+            eng = hit[0] if hit is not None else _eng.Engine(self.SCALE, mode, key[0])
+            eng.load_state_dict({k: v for k, v in self.state_dict().items()})
+            if wkey[1] is None and hit is not None:
+                wkey = (wkey[0], hit[1][1])
+            self._engines[key] = (eng, wkey)
         return eng
 
     # ---- the hot path -------------------------------------------------------------------------
@@ -97,7 +134,7 @@ class CODONNetBase(nn.Module):
         if not x.is_cuda:
             raise _eng.CodonError("CODONNet.forward needs CUDA tensors: codon_b200 has no CPU path "
                                   "(the reference's CPU forward lives in oracle/ as a test checker only)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise _eng.CodonError("codon_b200 is an inference engine: call model.eval() / torch.no_grad() "
                                   "(the reference test.py does, CODON_X4/test.py:67)")
         return self.engine(x.device).forward(x, y.to(x.dtype))
@@ -105,4 +142,10 @@ class CODONNetBase(nn.Module):
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_engines"] = {}
+        st["_engine_lock"] = None
+        st["_plist"] = None
         return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._engine_lock = threading.Lock()

@@ -15,16 +15,13 @@ Two levels:
   CODON_X4/test.py:140-145), NCCL over NVLink when launched one process per GPU, or nothing at all
   in the single-process multi-thread mode.
 
-This module holds the host-side part: the deterministic frame -> rank/GPU assignment, batching of
-same-shaped frames under a memory budget, a thread-per-GPU executor for single-process use, and the
-metric reduction.
+This module holds the host-side part: the deterministic frame -> rank/GPU assignment, a thread-per-GPU
+executor for single-process use, and the metric reduction.
 """
 from __future__ import annotations
 
 import threading
-from collections import defaultdict
-from dataclasses import dataclass
-from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -35,36 +32,6 @@ def shard_indices(n_items: int, world: int, rank: int) -> List[int]:
     if world < 1 or not (0 <= rank < world):
         raise ValueError(f"bad world/rank {world}/{rank}")
     return list(range(rank, n_items, world))
-
-
-@dataclass
-class Batch:
-    indices: List[int]          # positions in the caller's frame list
-    shape: Tuple[int, int]      # (H, W)
-
-
-def plan_batches(shapes: Sequence[Tuple[int, int]], indices: Iterable[int], max_pixels: int) -> List[Batch]:
-    """Groups frames of identical (H, W) into batches of at most ``max_pixels`` pixels per launch
-    (one C-ABI call per batch amortises launch overhead and fills the last tile wave).  Order inside
-    a shape group follows ``indices``; a frame larger than ``max_pixels`` still gets its own batch."""
-    groups: Dict[Tuple[int, int], List[int]] = defaultdict(list)
-    order: List[Tuple[int, int]] = []
-    for i in indices:
-        s = tuple(shapes[i])
-        if s not in groups:
-            order.append(s)
-        groups[s].append(i)
-    out: List[Batch] = []
-    for s in order:
-        per = max(1, max_pixels // (s[0] * s[1]))
-        g = groups[s]
-        for k in range(0, len(g), per):
-            out.append(Batch(g[k:k + per], s))
-    return out
-
-
-def max_pixels_for_budget(workspace_bytes_per_pixel: float, budget_bytes: int) -> int:
-    return max(1, int(budget_bytes // max(1.0, workspace_bytes_per_pixel)))
 
 
 def reduce_metric_sums(rmse_sum: float, ssim_sum: float, count: int,

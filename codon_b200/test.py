@@ -13,9 +13,13 @@ checkpoint name (:56) and is broken as shipped; here they are fl
   --label DIR        ground truth                         --fix DIR           hole-filled GT for SSIM (default: label)
   --out DIR          result PNGs (default CODON_result_save/)   --logfile F   tee of stdout (default ./test_sintel.txt)
   --pretrained FILE  X4.pth-style checkpoint; without it seeded synthetic weights are used (and said so)
+  --lr-depth DIR     TRUE low-resolution depth PNGs (H/s x W/s): uploaded as uint8 (s^2 fewer bytes) and upsampled
+                     to the guide's size on the GPU (cv2.INTER_CUBIC semantics) instead of reading the offline
+                     "Bicubic/X4" images of --input-depth (test.py:77)
 
-Everything between the PNG decode and the PNG encode runs on the GPU (forward, quantisation, RMSE,
-SSIM).  Images are sharded over the GPUs named by ``--gpus`` (one host thread per GPU), or over
+Everything between the PNG decode and the PNG encode runs on the GPU: the images are uploaded as uint8, the colour
+guide is converted to gray with the arithmetic of ``cv2.imread(path, 0)`` (test.py:118), ``/255`` (test.py:122-123),
+the optional bicubic up-sampling, the forward, the quantisation, RMSE and SSIM.  Images are sharded over the GPUs named by ``--gpus`` (one host thread per GPU), or over
 ranks when launched under torchrun; the sums are combined with one all-reduce.
 """
 from __future__ import annotations
@@ -45,6 +49,7 @@ parser.add_argument("--input-depth", default=None)
 parser.add_argument("--input-color", default=None)
 parser.add_argument("--label", default=None)
 parser.add_argument("--fix", default=None)
+parser.add_argument("--lr-depth", default=None, help="directory of true low-resolution depth PNGs (upsampled on the GPU)")
 parser.add_argument("--out", default="CODON_result_save/")
 parser.add_argument("--logfile", default="./test_sintel.txt", help="tee of stdout (reference: ./test_sintel.txt); empty = none")
 parser.add_argument("--seed", type=int, default=None)
@@ -59,6 +64,19 @@ def _imread_gray(path):
     img = cv2.imread(path, 0)                       # test.py:116-118
     if img is None:
         raise FileNotFoundError(path)
+    return img
+
+
+def _imread_any(path):
+    """uint8 [H,W] (single-channel file) or [H,W,3] BGR (colour file): the bytes cv2 decodes, no conversion."""
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if img is None:
+        raise FileNotFoundError(path)
+    if img.dtype != np.uint8:
+        return _imread_gray(path)
+    if img.ndim == 3 and img.shape[2] == 4:
+        img = np.ascontiguousarray(img[:, :, :3])
     return img
 
 
@@ -90,13 +108,22 @@ def _process(net, gpu, job, o):
     """One image on one GPU: returns (name, rmse, ssim)."""
     name, depth_path, gray_path, label_path, fix_path = job
     dev = torch.device("cuda", gpu)
-    depth_u8 = _imread_gray(depth_path)
-    gray_u8 = _imread_gray(gray_path)
     label_u8 = _imread_gray(label_path)
     fix_u8 = _imread_gray(fix_path) if fix_path != label_path else label_u8
     io_dtype = {"fp16": torch.float16, "bf16": torch.bfloat16}.get(o.mode, torch.float32)
-    x = torch.from_numpy(depth_u8 / 255).float()[None, None].to(dev).to(io_dtype)     # test.py:122
-    y = torch.from_numpy(gray_u8 / 255).float()[None, None].to(dev).to(io_dtype)      # test.py:123
+    # guide: the decoded bytes go up as uint8; a colour file is converted to gray on the GPU with the arithmetic of
+    # cv2.imread(path, 0) (test.py:118), then /255 (test.py:123)
+    guide = torch.from_numpy(_imread_any(gray_path)).to(dev)
+    gray_u8 = _eng.bgr_to_gray_u8(guide, "imread") if guide.dim() == 3 else guide
+    y = _eng.u8_to_unit_f32(gray_u8)[None, None].to(io_dtype)
+    H, W = gray_u8.shape
+    if getattr(o, "lr_depth", None):
+        # true LR depth (H/s x W/s uint8): /255 and bicubic up-sampling to the guide's size on the GPU
+        lr = torch.from_numpy(_imread_gray(os.path.join(o.lr_depth, name))).to(dev)
+        x = _eng.bicubic_upsample(_eng.u8_to_unit_f32(lr)[None], H, W).clamp_(0.0, 1.0)[None].to(io_dtype)
+    else:
+        depth_u8 = torch.from_numpy(_imread_gray(depth_path)).to(dev)                    # test.py:116
+        x = _eng.u8_to_unit_f32(depth_u8)[None, None].to(io_dtype)                       # test.py:122
     with torch.no_grad():
         out = net.engine(dev).forward(x, y)                                              # test.py:125
     # np.clip(out,0,1); (out*255).astype(uint8), evaluated in the output dtype (test.py:127-132)
@@ -172,9 +199,15 @@ def main(argv=None):
         from .checkpoint import load_checkpoint
         sd, meta = load_checkpoint(opt.pretrained)                                       # test.py:56-59
         opt.start_epoch = int(meta.get("epoch", 0)) + 1
-        missing = set(model.state_dict()) - set(sd)
-        # x16 checkpoints have no attention_c5/s5; x4/x8 ones do -- tolerate either
-        model.load_state_dict(sd, strict=not all(k.startswith(("attention_c5.", "attention_s5.")) for k in missing))
+        from .checkpoint import infer_scale
+        # x4/x8 checkpoints carry the never-called attention_c5 / attention_s5 (CODON_x4.py:64-65), x16 ones do not
+        # (SURVEY.md 5.4): the checkpoint must be of the family --scale names, and then every key must match
+        family = infer_scale(sd)
+        want = "x16" if opt.scale == 16 else "x4/x8"
+        if family != want:
+            raise _eng.CodonError(f"'{opt.pretrained}' is an {family} checkpoint but --scale {opt.scale} was given "
+                                  f"({'no ' if want == 'x16' else ''}attention_c5 / attention_s5 keys expected)")
+        model.load_state_dict(sd, strict=True)
         print(f"=> loaded '{opt.pretrained}' (epoch {meta.get('epoch', '?')})")
     else:
         from .synthetic import synthetic_state_dict

@@ -86,6 +86,16 @@ int codon_selftest(void);
 int codon_set_weight(codon_ctx* ctx, const char* name, const float* data,
                      const int64_t* shape, int ndim);
 int codon_finalize_weights(codon_ctx* ctx);
+/* Number of successful codon_finalize_weights calls on this context.  A re-finalize re-uses the device
+ * allocations of the previous one (same sizes), so pointers captured in a CUDA graph stay valid, but a graph also
+ * holds per-layer constants derived from the weights: holders of a captured forward compare this counter and
+ * re-capture when it has moved (codon_b200.engine.GraphedForward does). */
+unsigned long long codon_weights_generation(const codon_ctx* ctx);
+/* Replaces, for hosts without Python: torch.load('X4.pth') + load_state_dict (CODON_X4/test.py:56-59).  Reads a flat
+ * weight file written by codon_b200.checkpoint.export_flat (the importer turns the reference's pickled-module .pth
+ * into it), calls codon_set_weight for every tensor and codon_finalize_weights.  Format, little endian, unpadded:
+ *   "CODONW1\0" | uint32 n | n x { uint16 name_len | name | uint8 ndim | ndim x int64 dims | prod(dims) x float32 } */
+int codon_load_weights_file(codon_ctx* ctx, const char* path);
 
 /* Bytes of device scratch codon_forward needs for B frames of H x W (activations live here
  * so that the memory stays owned by and visible to the caller's allocator). */

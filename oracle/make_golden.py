@@ -14,8 +14,16 @@ cannot travel to the GPU box, so its outputs on fixed inputs are committed as fi
   tests/golden/preproc.npz    cv2 gray conversion of a colour crop; cv2.resize(INTER_CUBIC) of LR depth crops
   tests/golden/metrics.json   EvaluationResults (test.py:148-164, exec'd from source lines) and
                               ssim_2.ssim_exact on those images
+  tests/golden/images/ref_fp32_x{4,8,16}/  the reference's fp32 CPU forward (synthetic seed-0 weights) on the 30
+                              bundled input pairs, quantised with the driver rule (test.py:130-132) -> uint8 PNG,
+                              and tests/golden/image_parity.json = its EvaluationResults / ssim_exact vs the label:
+                              the north_star's "RMSE/SSIM identical to 3 decimals" is asserted against these
+  tests/golden/big_*.npz      the reference forward at the BASELINE.json shapes (640x480, 8 x 640x480, 1280x720,
+                              1920x1080; fp32 and fp64): row sums, column sums, a stride-4 sample and full-resolution
+                              crops of the output (the whole frames would be tens of MB)
 
-Usage:  python oracle/make_golden.py            (needs /root/reference)
+Usage:  python oracle/make_golden.py [all|images|big|small]   (needs /root/reference)
+
 """
 import importlib
 import json
@@ -148,20 +156,6 @@ def copy_images_and_metrics():
         print(f"x{s}: mean RMSE {r:.4f} SSIM {q:.4f}")
 
 
-if __name__ == "__main__":
-    os.makedirs(GOLD, exist_ok=True)
-    torch.set_num_threads(os.cpu_count())
-    copy_images_and_metrics()
-    run_cac()
-    run_forward(4, 0, (2, 48, 64), "x4_s0_b2_48x64", 1234)
-    run_forward(4, 1, (1, 37, 53), "x4_s1_b1_37x53", 77)
-    run_forward(8, 2, (1, 40, 72), "x8_s2_b1_40x72", 5)
-    run_forward(16, 2, (1, 64, 80), "x16_s2_b1_64x80", 99)
-    run_forward(4, 0, (1, 120, 160), "x4_s0_b1_120x160", 4321)
-    run_image_forward(4, 0, "Tsukuba.png", "x4_s0_tsukuba")
-    run_preproc()
-
-
 def run_preproc():
     """Fixtures for the GPU pre-processing kernels: cv2's own gray conversion of a decoded colour image
     (what cv2.imread(path, 0) returns, test.py:118) and cv2.resize(INTER_CUBIC) on float32."""
@@ -186,3 +180,115 @@ def run_preproc():
         out[f"up_x{s}"] = up
     np.savez_compressed(os.path.join(GOLD, "preproc.npz"), **out)
     print("preproc fixtures written")
+
+
+def run_image_parity_refs():
+    """The reference's own fp32 result on every bundled input pair, as the uint8 image its driver would write
+    (test.py:122-132: /255 -> float -> forward -> clip -> *255 -> astype(uint8)) and the two metrics of that image."""
+    import cv2
+    rmse_fn = reference_rmse_fn()
+    img_dir = os.path.join(GOLD, "images")
+    names = sorted(os.listdir(os.path.join(img_dir, "gray")))
+    table = {}
+    for scale in (4, 8, 16):
+        mod, _, ssim2, _ = load_reference(scale)
+        net = mod.CODONNet().eval()
+        net.load_state_dict(orc.synthetic_state_dict(scale, 0), strict=True)
+        os.makedirs(os.path.join(img_dir, f"ref_fp32_x{scale}"), exist_ok=True)
+        for n in names:
+            d = cv2.imread(os.path.join(img_dir, f"depth_x{scale}", n), 0)
+            g = cv2.imread(os.path.join(img_dir, "gray", n), 0)
+            lab = cv2.imread(os.path.join(img_dir, "label", n), 0)
+            x = torch.from_numpy(d / 255).float()[None, None]
+            y = torch.from_numpy(g / 255).float()[None, None]
+            with torch.no_grad():
+                out = net(x, y).squeeze().numpy()
+            out = np.clip(out, 0, 1)
+            q = (out * 255).astype(np.uint8)
+            cv2.imwrite(os.path.join(img_dir, f"ref_fp32_x{scale}", n), q, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+            table[f"x{scale}/{n}"] = {"rmse": rmse_fn(lab, q), "ssim": float(ssim2.ssim_exact(lab / 255, q / 255))}
+            print(f"image parity ref x{scale} {n}: rmse {table[f'x{scale}/{n}']['rmse']:.4f} ssim {table[f'x{scale}/{n}']['ssim']:.5f}", flush=True)
+    json.dump(table, open(os.path.join(GOLD, "image_parity.json"), "w"), indent=1, sort_keys=True)
+
+
+BIG_CROP = 96
+
+
+def big_summary(out):
+    """Size-bounded fingerprint of a [H, W] output: row / column sums (fp64), a stride-4 sample, five crops."""
+    H, W = out.shape
+    o = out.astype(np.float64)
+    c = BIG_CROP
+    ys = (0, H - c, (H - c) // 2)
+    xs = (0, W - c, (W - c) // 2)
+    crops = {"tl": out[:c, :c], "tr": out[:c, W - c:], "bl": out[H - c:, :c], "br": out[H - c:, W - c:],
+             "ce": out[ys[2]:ys[2] + c, xs[2]:xs[2] + c]}
+    return {"row_sum": o.sum(1), "col_sum": o.sum(0), "sample4": out[1::4, 2::4].copy(), **{f"crop_{k}": v.copy() for k, v in crops.items()}}
+
+
+def run_big(scale, seed, shape, name, frame_seed, frames=(0,), with_fp64=True):
+    """Reference forward at a BASELINE.json shape; stores fingerprints of the frames listed in `frames`."""
+    mod, _, _, _ = load_reference(scale)
+    sd = orc.synthetic_state_dict(scale, seed)
+    b, h, w = shape
+    x, y = orc.synthetic_frames(b, h, w, frame_seed)
+    net = mod.CODONNet().eval()
+    net.load_state_dict(sd, strict=True)
+    rec = {"scale": scale, "seed": seed, "frame_seed": frame_seed, "shape": np.array(shape), "frames": np.array(frames),
+           "x_sum": x.double().sum(dim=(1, 2, 3)).numpy(), "y_sum": y.double().sum(dim=(1, 2, 3)).numpy()}
+    with torch.no_grad():
+        out32 = net(x, y).numpy()
+        for f in frames:
+            for k, v in big_summary(out32[f, 0]).items():
+                rec[f"f{f}_fp32_{k}"] = v
+        if with_fp64:
+            out64 = net.double()(x.double(), y.double()).numpy()
+            for f in frames:
+                for k, v in big_summary(out64[f, 0]).items():
+                    rec[f"f{f}_fp64_{k}"] = v
+            print(f"big_{name}: fp32-vs-fp64 max-abs {np.abs(out32 - out64).max():.2e}", flush=True)
+    np.savez_compressed(os.path.join(GOLD, f"big_{name}.npz"), **rec)
+    print(f"big_{name}: x{scale} seed {seed} {shape} done", flush=True)
+
+
+def write_c_case(npz_name, out_name):
+    """A committed forward golden (real reference output) in the raw layout examples/c_consumer.c reads:
+    "CODONC1\\0" | int32 B, H, W | x | y | out_fp32   (float32, little endian)."""
+    import struct
+    g = np.load(os.path.join(GOLD, npz_name))
+    x, y, out = g["x"], g["y"], g["out_fp32"]
+    b, _, h, w = x.shape
+    with open(os.path.join(GOLD, out_name), "wb") as f:
+        f.write(b"CODONC1\0")
+        f.write(struct.pack("<3i", b, h, w))
+        for a in (x, y, out):
+            f.write(np.ascontiguousarray(a, dtype="<f4").tobytes())
+    print(f"{out_name}: {b}x{h}x{w}")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "c_case":
+        write_c_case("fwd_x4_s0_b2_48x64.npz", "c_case_x4_s0_b2_48x64.bin")
+    if what in ("all", "small"):
+        copy_images_and_metrics()
+        run_cac()
+        run_forward(4, 0, (2, 48, 64), "x4_s0_b2_48x64", 1234)
+        run_forward(4, 1, (1, 37, 53), "x4_s1_b1_37x53", 77)
+        run_forward(8, 2, (1, 40, 72), "x8_s2_b1_40x72", 5)
+        run_forward(16, 2, (1, 64, 80), "x16_s2_b1_64x80", 99)
+        run_forward(4, 0, (1, 120, 160), "x4_s0_b1_120x160", 4321)
+        run_image_forward(4, 0, "Tsukuba.png", "x4_s0_tsukuba")
+        run_preproc()
+        write_c_case("fwd_x4_s0_b2_48x64.npz", "c_case_x4_s0_b2_48x64.bin")
+    if what in ("all", "images"):
+        run_image_parity_refs()
+    if what in ("all", "big"):
+        # BASELINE.json configs[1..4]: x4 640x480; x8 batch of 8 x 640x480 (one GPU's shard of the 64);
+        # x16 1920x1080; 1280x720 (x4 here; configs[4] cycles the scales)
+        run_big(4, 0, (1, 480, 640), "x4_640x480", 1234)
+        run_big(8, 1, (8, 480, 640), "x8_b8_640x480", 2000, frames=(0, 7))
+        run_big(4, 2, (1, 720, 1280), "x4_1280x720", 3000)
+        run_big(16, 0, (1, 1080, 1920), "x16_1920x1080", 4000)

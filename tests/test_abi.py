@@ -81,7 +81,7 @@ def test_module_surface_matches_reference_inventory():
     assert CODON_x4.CODONNet().mode == "fp32"
 
 
-def _build_c_consumer(tmp_path):
+def _build_c_consumer(tmp_path, args=()):
     import shutil
     import subprocess
     gcc = shutil.which("gcc")
@@ -91,10 +91,11 @@ def _build_c_consumer(tmp_path):
     exe = str(tmp_path / "c_consumer")
     libdir = os.path.join(ROOT, "codon_b200")
     cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "examples", "c_consumer.c"), "-o", exe, "-L" + libdir, "-lcodon_b200", "-Wl,-rpath," + libdir]
+           os.path.join(ROOT, "examples", "c_consumer.c"), "-o", exe, "-L" + libdir, "-lcodon_b200", "-Wl,-rpath," + libdir,
+           "-lm"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr                               # the header is plain C99, no C++-isms
-    return subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    return subprocess.run([exe, *args], capture_output=True, text=True, timeout=300)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -109,3 +110,20 @@ def test_plain_c_consumer_on_gpu(tmp_path):
     r = _build_c_consumer(tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "refused as documented" in r.stdout and r.stdout.strip().endswith("ok")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,tol", [(4, 2e-6), (0, 1e-4), (2, 1e-3), (1, 2e-2)])
+def test_forward_from_plain_c_matches_reference(tmp_path, mode, tol):
+    """A non-Python host end to end: the flat weight file exported by checkpoint.export_flat is
+    loaded by codon_load_weights_file, codon_forward_host runs on the committed frames, and the C program itself
+    compares with the real reference's output (tests/golden/c_case_*.bin, oracle/make_golden.py)."""
+    import codon_oracle as orc
+    from codon_b200 import checkpoint as ck
+    wpath = str(tmp_path / "x4_s0.codonw")
+    assert ck.export_flat(orc.synthetic_state_dict(4, 0), wpath) == 49
+    case = os.path.join(ROOT, "tests", "golden", "c_case_x4_s0_b2_48x64.bin")
+    r = _build_c_consumer(tmp_path, (wpath, case, str(mode), repr(tol)))
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "forward from C: 2 x 48 x 64" in r.stdout and r.stdout.strip().endswith("ok")

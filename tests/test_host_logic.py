@@ -25,14 +25,6 @@ def test_shard_indices_partition():
         sch.shard_indices(4, 2, 2)
 
 
-def test_plan_batches_groups_by_shape_and_budget():
-    shapes = [(480, 640)] * 5 + [(370, 463)] * 2 + [(1080, 1920)]
-    b = sch.plan_batches(shapes, range(len(shapes)), max_pixels=2 * 480 * 640)
-    assert [x.indices for x in b] == [[0, 1], [2, 3], [4], [5, 6], [7]]
-    assert b[-1].shape == (1080, 1920)
-    assert sch.max_pixels_for_budget(1800.0, 18_000_000) == 10_000
-
-
 def _reduce_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -96,6 +88,83 @@ def test_checkpoint_import_reference_style():
         got2, _ = ck.load_checkpoint(p2)
         assert got2.keys() == sd.keys()
     assert ck.infer_scale(orc.synthetic_state_dict(4, 0)) == "x4/x8"
+
+
+def test_flat_weight_file_roundtrip(tmp_path):
+    """checkpoint.export_flat / load_flat: the file codon_load_weights_file reads (layout pinned byte for byte)."""
+    import struct
+    sd = {"module." + k: v for k, v in orc.synthetic_state_dict(16, 3).items()}
+    path = str(tmp_path / "w.codonw")
+    assert ck.export_flat(sd, path) == 44
+    back = ck.load_flat(path)
+    assert list(back) == [k[len("module."):] for k in sd]
+    assert all(torch.equal(back[k[len("module."):]], v) for k, v in sd.items())
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"CODONW1\0" and struct.unpack("<I", raw[8:12])[0] == 44
+    first = next(iter(back))
+    (ln,) = struct.unpack("<H", raw[12:14])
+    assert raw[14:14 + ln].decode() == first and raw[14 + ln] == back[first].dim()
+    with pytest.raises(ValueError):
+        open(path, "wb").write(b"garbage!" + raw[8:])
+        ck.load_flat(path)
+
+
+def test_unpickler_does_not_import_foreign_modules(tmp_path):
+    """A checkpoint naming a class of an importable non-torch module must get a stub, not an import (the module is
+    never executed), and the tensors must still come out."""
+    marker = tmp_path / "imported.flag"
+    pkg = tmp_path / "evil_zoo.py"
+    pkg.write_text("import pathlib\n"
+                   f"pathlib.Path({str(marker)!r}).write_text('x')\n"
+                   "import torch.nn as nn\n"
+                   "class Net(nn.Module):\n"
+                   "    def __init__(self):\n"
+                   "        super().__init__()\n"
+                   "        self.conv1 = nn.Conv2d(64, 64, 3, bias=False)\n")
+    sys.path.insert(0, str(tmp_path))
+    try:
+        import importlib
+        zoo = importlib.import_module("evil_zoo")
+        net = zoo.Net()
+        p = str(tmp_path / "m.pth")
+        torch.save({"epoch": 1, "model": net}, p)
+        del sys.modules["evil_zoo"]
+        marker.unlink()
+        got, meta = ck.load_checkpoint(p)                 # evil_zoo is importable from sys.path -- and must not be
+        assert not marker.exists() and "evil_zoo" not in sys.modules
+        assert list(got) == ["conv1.weight"] and torch.equal(got["conv1.weight"], net.conv1.weight.data)
+    finally:
+        sys.path.remove(str(tmp_path))
+
+
+def test_model_weight_versioning_without_gpu():
+    """CODONNet tracks weight changes by version (load_state_dict, .half()/.to(), in-place ops on the parameters,
+    refresh_weights() for edits through .data); DataParallel replicas trust the master's counter."""
+    from codon_b200.CODON_x4 import CODONNet
+    net = CODONNet().eval()
+    k0 = net._weights_key()
+    assert net._weights_key() == k0
+    net.load_state_dict(orc.synthetic_state_dict(4, 0))
+    k1 = net._weights_key()
+    assert k1 != k0
+    with torch.no_grad():
+        net.conv3.weight.mul_(2.0)
+    k2 = net._weights_key()
+    assert k2 != k1
+    net.conv3.weight.data.mul_(0.5)                      # not versioned by PyTorch ...
+    assert net._weights_key() == k2
+    net.refresh_weights()                                # ... hence the explicit call
+    k3 = net._weights_key()
+    assert k3 != k2
+    net.half()
+    assert net._weights_key() != k3 and net.mode == "fp16"
+    rep = net._replicate_for_data_parallel()
+    rep._is_replica = True
+    assert rep._weights_key() == (net._wver, None) and rep._engines is net._engines
+    import copy
+    import pickle
+    assert copy.deepcopy(net)._weights_key()[0] == net._wver
+    assert pickle.loads(pickle.dumps(net)).state_dict().keys() == net.state_dict().keys()
 
 
 def test_logger_tees(capsys):

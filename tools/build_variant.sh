@@ -1,12 +1,19 @@
 #!/bin/bash
 # Builds an experimental variant of the library: tools/build_variant.sh <name> [-DFLAG ...] -> build/variants/lib_<name>.so
+# (objects are cached under build/obj; conv_tc is recompiled when its sources or the variant's flags changed)
 set -e
 NAME=$1; shift
 FL="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 C=codon_b200/csrc
+mkdir -p build/obj build/variants
+newest_hdr=$(ls -t $C/*.h $C/*.cuh include/*.h | head -1)
 for f in api conv_direct cac cac_nchw edge metrics preproc; do
-  if [ ! -f build/obj/$f.o ] || [ $C/$f.cu -nt build/obj/$f.o ]; then nvcc $FL -c -o build/obj/$f.o $C/$f.cu; fi
+  if [ ! -f build/obj/$f.o ] || [ $C/$f.cu -nt build/obj/$f.o ] || [ $newest_hdr -nt build/obj/$f.o ]; then nvcc $FL -c -o build/obj/$f.o $C/$f.cu; fi
 done
-nvcc $FL "$@" -c -o build/obj/conv_tc_$NAME.o $C/conv_tc.cu 2>&1 | grep -E "error" || true
-nvcc -shared -o build/variants/lib_$NAME.so build/obj/{api,conv_direct,cac,cac_nchw,edge,metrics,preproc}.o build/obj/conv_tc_$NAME.o
+O=build/obj/conv_tc_$NAME.o
+if [ ! -f $O ] || [ $C/conv_tc.cu -nt $O ] || [ $newest_hdr -nt $O ] || [ "$(cat $O.flags 2>/dev/null)" != "$*" ]; then
+  nvcc $FL "$@" -c -o $O $C/conv_tc.cu 2>&1 | grep -E "error" || true
+  echo "$*" > $O.flags
+fi
+nvcc -shared -o build/variants/lib_$NAME.so build/obj/{api,conv_direct,cac,cac_nchw,edge,metrics,preproc}.o $O
 ls -la build/variants/lib_$NAME.so

@@ -217,6 +217,25 @@ int main(int argc, char** argv) {
   cudaMalloc(&d_out, 1024 * sizeof(unsigned long long));
   int rc = 0;
   if (argc > 2 && atoi(argv[2]) == 1) { rc |= sweep<2>(128, iters, sms, d_out); rc |= sweep<1>(128, iters, sms, d_out); return rc; }
+  if (argc > 2 && atoi(argv[2]) == 3) {
+    // A-patch row pitch (the descriptor's 8-row-group stride): 1024 = contiguous, 1536 = 12-pixel patch (8-pixel-wide
+    // tile + 5x5 halo: the NACC = 1 geometry), 1280 (8 + 3x3 halo), 2560 = 20-pixel patch (NACC = 2), 2304 (16 + 3x3)
+    for (int sbo : {1024, 1280, 1536, 2048, 2304, 2560, 3072}) {
+      char label[160];
+      RateParams p = {};
+      p.n = 128; p.m = 256; p.b_rows = 64; p.sbo = sbo; p.shift = 1; p.commit_each = 1; p.data = 2;
+      p.nacc = 1; p.iters = iters * 2;
+      snprintf(label, sizeof label, "bf16 cg2 M256 N128 nacc1 sbo %d shift", sbo);
+      rc |= run<2, 1, 0>(label, p, sms & ~1, d_out);
+      p.shift = 0;
+      snprintf(label, sizeof label, "bf16 cg2 M256 N128 nacc1 sbo %d fixed", sbo);
+      rc |= run<2, 1, 0>(label, p, sms & ~1, d_out);
+      p.n = 64; p.b_rows = 32; p.shift = 1;
+      snprintf(label, sizeof label, "bf16 cg2 M256 N64  nacc1 sbo %d shift", sbo);
+      rc |= run<2, 1, 0>(label, p, sms & ~1, d_out);
+    }
+    return rc;
+  }
   if (argc > 2 && atoi(argv[2]) == 2) { for (int n : {16, 32, 48, 64, 96}) { rc |= sweep<2>(n, iters, sms, d_out); rc |= sweep<1>(n, iters, sms, d_out); } return rc; }
   for (int n : {64, 128, 256}) rc |= sweep<2>(n, iters, sms, d_out);
   for (int n : {64, 128, 256}) rc |= sweep<1>(n, iters, sms, d_out);
