@@ -2,7 +2,7 @@
 """Benchmark of the CODON forward pass on B200 (metric: HR depth megapixels per second).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                  [--mode tf32|fp32|fp16|bf16] [--scale 4|8|16] [--frames F] [--height H] [--width W]
+                  [--mode tf32|f16x3|fp32|fp16|bf16] [--scale 4|8|16] [--frames F] [--height H] [--width W]
 
 A step is one forward pass over one batch of F synthetic frames per GPU.  The default workload is
 BASELINE.json configs[1]: CODON x4, a single 640x480 frame, "fp32 parity mode" (mode tf32: fp32
@@ -14,16 +14,18 @@ max-over-ranks timing only.
 
 One JSON line is printed by rank 0 (see the driver contract in the task description):
   value        device-timed throughput, frames resident in HBM (CUDA events, max over ranks)
-  e2e          the same metric through the host entry points: every step copies its two frames from
-               pinned host memory and its result back inside the timed region.  Headline = the
-               streaming form (codon_forward_host_submit / _wait, one call submitted ahead: copies
-               overlap the neighbouring call's kernels); e2e.blocking_call = one codon_forward_host
-               per step, nothing overlapped
+  e2e          the same metric through the drop-in call the reference's driver makes (CODON_X4/test.py:122-128):
+               pinned host frames -> .cuda() -> CODONNet.forward (codon_b200.CODON_x4.CODONNet, one codon_forward
+               call) -> .cpu(), every step inside the timed region.  e2e.streaming = the library's streaming
+               host entry points (codon_forward_host_submit / _wait, one call submitted ahead: copies overlap the
+               neighbouring call's kernels); e2e.blocking_call = one codon_forward_host per step
   roofline     dominant kernel (5x5 128->128 tcgen05 implicit GEMM with the fused 1x1): algorithmic FLOP
                of the 5x5 alone / CUDA-event time of its launches, against MEASURED_PEAKS.json.  The
                per-launch events are recorded over a second pass of the same K steps: events between the
                launches serialise them, and `value` times the forward as a caller runs it.
-  cpu_baseline the oracle's CPU forward (torch fp32, all host cores) on a bounded sample
+  cpu_baseline the reference's own CPU forward (its CODONNet class from oracle/_ref, torch fp32, all host cores;
+               kind "reference") -- or the oracle's restatement of it (kind "port") when oracle/_ref was never
+               built -- on a bounded sample
 --impl reference times that CPU forward alone, as the reference arm.
 """
 from __future__ import annotations
@@ -46,7 +48,10 @@ IDLE_S = 1.5
 METRIC = "hr_depth_megapixels_per_second"
 UNIT = "MP/s"
 DTYPE_NAME = {"fp32": "f32", "tf32": "f32 (tf32 tensor-core products, f32 accumulate)",
+              "f16x3": "f32-accurate (split f16 hi+lo operands, 3 tensor-core MMAs per K step, f32 accumulate)",
               "fp16": "f16 operands, f32 accumulate", "bf16": "bf16 operands, f32 accumulate"}
+# tensor-core MMA work per algorithmic FLOP (f16x3 issues hi*hi + lo*hi + hi*lo)
+MMA_FACTOR = {"fp32": 1.0, "tf32": 1.0, "f16x3": 3.0, "fp16": 1.0, "bf16": 1.0}
 
 
 def parse_args():
@@ -55,7 +60,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="codon_b200", choices=["codon_b200", "reference"])
-    ap.add_argument("--mode", default="tf32", choices=["fp32", "tf32", "fp16", "bf16"])
+    ap.add_argument("--mode", default="tf32", choices=["fp32", "tf32", "f16x3", "fp16", "bf16"])
     ap.add_argument("--scale", type=int, default=4, choices=[4, 8, 16])
     ap.add_argument("--frames", type=int, default=1, help="frames per GPU per step")
     ap.add_argument("--height", type=int, default=480)
@@ -71,6 +76,13 @@ def parse_args():
 def workload_name(a):
     return (f"CODON x{a.scale}, {a.frames} x {a.width}x{a.height} synthetic RGB-D frame(s) per GPU per step, "
             f"mode {a.mode}")
+
+
+def config_dict(a):
+    """The `config` object of BOTH arms (the driver compares them key by key): what is measured, not how."""
+    return {"workload": workload_name(a), "scale": a.scale, "frames_per_gpu": a.frames, "height": a.height, "width": a.width,
+            "mode": a.mode, "weights": "synthetic seed 0 (reference init, output.weight x0.002)",
+            "sharding": "independent frames per rank, no data-path collective"}
 
 
 def load_peaks():
@@ -151,23 +163,35 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU leg (oracle; the only place bench.py touches oracle/)
 
-def cpu_forward_sample(scale, height, width, budget_s, steps, warmup):
-    """Times the oracle's fp32 CPU forward (a functional restatement of the reference's PyTorch
-    forward; the reference itself is Python under /root/reference and cannot travel to the GPU box)
-    on a bounded sample: the top `rows` rows of one frame of the workload, rows chosen so that
-    (steps + warmup) forwards fit `budget_s`.  Returns (MP/s, description, cores, out, rows)."""
-    import torch
+def cpu_forward_fn(scale):
+    """The CPU forward the CPU legs time: the reference's own `CODONNet` (oracle/_ref, built from /root/reference by
+    oracle/build_ref.py; kind "reference"), else the oracle's restatement (kind "port").  Returns (fn(x, y), kind, orc)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import codon_oracle as orc
+    import build_ref
+    sd = orc.synthetic_state_dict(scale, 0)
+    cls = build_ref.load_model_class(scale)
+    if cls is not None:
+        net = cls().eval()
+        net.load_state_dict(sd, strict=True)
+        return (lambda x, y: net(x, y)), "reference", orc
+    return (lambda x, y: orc.forward(sd, x, y)), "port", orc
+
+
+def cpu_forward_sample(scale, height, width, budget_s, steps, warmup):
+    """Times the reference's fp32 CPU forward (see cpu_forward_fn) on a bounded sample: the top `rows` rows of one
+    frame of the workload, rows chosen so that (steps + warmup) forwards fit `budget_s`.
+    Returns (MP/s, description, cores, out, rows, mean seconds, kind)."""
+    import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = orc.synthetic_state_dict(scale, 0)
+    fwd, kind, orc = cpu_forward_fn(scale)
     x, y = orc.synthetic_frames(1, height, width, 1234)
     probe_rows = min(height, 96)
     with torch.no_grad():
-        orc.forward(sd, x[:, :, :probe_rows], y[:, :, :probe_rows])          # oneDNN primitive warm-up
+        fwd(x[:, :, :probe_rows], y[:, :, :probe_rows])          # oneDNN primitive warm-up
         t0 = time.perf_counter()
-        orc.forward(sd, x[:, :, :probe_rows], y[:, :, :probe_rows])
+        fwd(x[:, :, :probe_rows], y[:, :, :probe_rows])
         rate = probe_rows * width / (time.perf_counter() - t0)               # px/s
     rows = int(min(height, max(32, budget_s * rate / max(1, steps + warmup) / width)))
     xs, ys = x[:, :, :rows].contiguous(), y[:, :, :rows].contiguous()
@@ -175,29 +199,27 @@ def cpu_forward_sample(scale, height, width, budget_s, steps, warmup):
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            out = orc.forward(sd, xs, ys)
+            out = fwd(xs, ys)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     mean_s = sum(times) / len(times)
-    desc = (f"{steps} timed forward(s) after {warmup} warm-up on the top {rows} of {height} rows of one "
+    what = "the reference's CODONNet class (oracle/_ref)" if kind == "reference" else "the oracle's restatement of the reference forward"
+    desc = (f"{what}: {steps} timed forward(s) after {warmup} warm-up on the top {rows} of {height} rows of one "
             f"{width}x{height} frame (x{scale} synthetic weights seed 0, torch {torch.__version__} fp32, {cores} threads)")
-    return rows * width / 1e6 / mean_s, desc, cores, out, rows, mean_s
+    return rows * width / 1e6 / mean_s, desc, cores, out, rows, mean_s, kind
 
 
 def run_reference_bundled(a):
     """BASELINE configs[0]: the reference's CPU path on the bundled images.  The .pth files are absent from the
     reference checkout, so the weights are the synthetic seed-0 set (image quality is meaningless; the timing
     and the pipeline are what is measured).  Loop semantics of CODON_X4/test.py:109-145."""
-    import numpy as np
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import codon_oracle as orc
     import cv2
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    fwd, kind, orc = cpu_forward_fn(a.scale)
     img = os.path.join(ROOT, "tests", "golden", "images")
     names = sorted(os.listdir(os.path.join(img, "gray")))
-    sd = orc.synthetic_state_dict(a.scale, 0)
     rmse_sum = ssim_sum = 0.0
     px = 0
     t_fwd = 0.0
@@ -209,7 +231,7 @@ def run_reference_bundled(a):
         y = torch.from_numpy(g / 255).float()[None, None]
         t0 = time.perf_counter()
         with torch.no_grad():
-            out = orc.forward(sd, x, y)[0, 0].numpy()
+            out = fwd(x, y)[0, 0].numpy()
         t_fwd += time.perf_counter() - t0
         q = orc.quantise_output(out)
         r, s_ = orc.masked_rmse(lab, q), orc.ssim_gauss(lab / 255, q / 255)
@@ -224,7 +246,7 @@ def run_reference_bundled(a):
                       "steps": len(names), "warmup": 0, "ms_per_step": t_fwd / len(names) * 1e3, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "bundled Middlebury images, synthetic weights",
                       "config": {"workload": f"BASELINE configs[0]: CODON x{a.scale} CPU forward over the 10 bundled images"},
-                      "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": "port",
+                      "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": kind,
                                        "sample": f"{len(names)} bundled images, forward only, {cores} threads"},
                       "mean_rmse": rmse_sum / len(names), "mean_ssim": ssim_sum / len(names),
                       "e2e": {"value": mps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -238,13 +260,13 @@ def run_reference(a):
     if a.bundled:
         return run_reference_bundled(a)
     steps, warmup = max(1, a.steps), max(0, a.warmup)
-    mps, desc, cores, _, rows, mean_s = cpu_forward_sample(a.scale, a.height, a.width, 150.0, steps, warmup)
+    mps, desc, cores, _, rows, mean_s, kind = cpu_forward_sample(a.scale, a.height, a.width, 150.0, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": mps, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "timing": "host wall clock around the CPU forward"},
-        "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "config": config_dict(a), "timing": "host wall clock around the CPU forward (fp32 whatever --mode says)",
+        "cpu_baseline": {"value": mps, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": mps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -279,6 +301,30 @@ def time_mode(eng, x, y, out, steps, warmup, flush, dist_barrier, profile=False)
         eng.profile_enable(False)
         prof = eng.profile_read()
     return sum(s.elapsed_time(e) for s, e in zip(starts, ends)), prof
+
+
+def measure_cublas_peak(dev, kind: str, n: int = 8192, reps: int = 20):
+    """Dense GEMM rate of cuBLAS on this GPU, now: bf16, or fp32 inputs with TF32 tensor-core products."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        dt = torch.bfloat16 if kind == "bf16" else torch.float32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a_ = torch.randn(n, n, device=dev, dtype=dt)
+        b_ = torch.randn(n, n, device=dev, dtype=dt)
+        for _ in range(3):
+            torch.matmul(a_, b_)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a_, b_)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        tf = 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) / 1e3) / 1e12
+        return {"tflops": tf, "kind": kind, "how": f"torch.matmul {n}^3 x {reps} (cuBLAS), CUDA events, this run"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def run_gpu(a):
@@ -320,8 +366,12 @@ def run_gpu(a):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     steps, warmup = max(1, a.steps), max(3, a.warmup)
 
-    eng = E.Engine(a.scale, a.mode, local)
-    eng.load_state_dict(sd)
+    # the drop-in module (codon_b200.CODON_x4 / _x8 / _x16 . CODONNet) owns the engine: every number below is measured on
+    # the engine a user of the reference's module surface gets
+    from importlib import import_module
+    net = import_module(f"codon_b200.CODON_x{a.scale}").CODONNet().eval().set_mode(a.mode)
+    net.load_state_dict(sd)
+    eng = net.engine(dev)
 
     # ---- device-timed throughput + per-kernel-class profile ---------------------------------------
     with ClockSampler(local) as clk:
@@ -367,12 +417,40 @@ def run_gpu(a):
         e2e_s = time.perf_counter() - t0
         barrier()
         assert np.array_equal(res, res2)
+        # (c) THE HEADLINE e2e: the reference driver's own sequence around the model call (CODON_X4/test.py:122-128) with
+        # the drop-in module -- pinned host frames -> .cuda() -> model(x, y) -> .cpu() -- every step
+        xp, yp = torch.from_numpy(xn), torch.from_numpy(yn)           # views of the pinned buffers
+        rp = torch.from_numpy(res)
+
+        def dropin_step():
+            with torch.no_grad():
+                o = net(xp.to(dev, non_blocking=True), yp.to(dev, non_blocking=True))       # test.py:122-125
+            rp.copy_(o, non_blocking=True)                                                  # test.py:127-128 (.cpu())
+            torch.cuda.synchronize(dev)
+        clk.idle(IDLE_S)
+        for _ in range(3):
+            dropin_step()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            dropin_step()
+        e2e_dropin_s = time.perf_counter() - t0
+        barrier()
+        assert np.array_equal(res, res2)
+        # host overhead of the module surface alone: CODONNet.forward vs Engine.forward on resident frames
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            for _ in range(200):
+                net.engine(dev)
+            key_us = (time.perf_counter() - t0) / 200 * 1e6
     total_ms = max_over_ranks(total_ms)
     prof_ms = max_over_ranks(prof_ms)
     e2e_s = max_over_ranks(e2e_s)
     e2e_blocking_s = max_over_ranks(e2e_blocking_s)
+    e2e_dropin_s = max_over_ranks(e2e_dropin_s)
     value = world * P * steps / 1e6 / (total_ms / 1e3)
-    e2e_value = world * P * steps / 1e6 / e2e_s
+    e2e_value = world * P * steps / 1e6 / e2e_dropin_s
     # CODON_TC_DEBUG knobs (kernel perf experiments) produce garbage on purpose; never set for a bench line
     assert os.environ.get("CODON_TC_DEBUG", "0") != "0" or np.isfinite(res).all()
 
@@ -385,6 +463,10 @@ def run_gpu(a):
     apply_ms, apply_bytes = prof["cac_apply"]["ms"], prof["cac_apply"]["work"]
     all_ms = sum(v["ms"] for v in prof.values())
     peak_tf = peaks["bf16_tflops"]
+    # the tensor-core rate of this mode's MMA kind, measured in this run with cuBLAS (torch.matmul): kind::tf32 for the
+    # tf32 mode, 16-bit otherwise (f16x3 issues three 16-bit MMAs per algorithmic multiply-add: MMA_FACTOR)
+    measured_peak = measure_cublas_peak(dev, "tf32" if a.mode == "tf32" else "bf16") if a.mode != "fp32" else None
+    mma_tfs = tfs * MMA_FACTOR[a.mode]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -393,12 +475,17 @@ def run_gpu(a):
         "kernel": "conv_tc2_kernel<FUSE> (5x5 128->128 implicit GEMM + ReLU + fused 1x1 128->64, tcgen05 cta_group::2)",
         "bound": "tensor",
         "achieved": tfs, "peak": peak_tf, "unit": "TFLOP/s", "frac": tfs / peak_tf,
-        "traffic": traffic["bytes"] if traffic else None, "traffic_detail": traffic,
+        "traffic": traffic["bytes"] if traffic else None,
+        "traffic_detail": traffic if traffic else "no ncu --set full capture of this workload is committed (profiles/traffic.json "
+                                                  "holds the captured ones, keyed mode|frames|HxW)",
         "peak_source": peaks["source"] + ", dense bf16 burst" +
-                       ("; tf32 runs at half the bf16 rate, so frac <= 0.5 in this mode" if a.mode == "tf32" else ""),
-        "peak_for_this_dtype": peak_tf / 2 if a.mode == "tf32" else peak_tf,
-        "frac_of_dtype_peak": tfs / (peak_tf / 2 if a.mode == "tf32" else peak_tf),
-        "frac_of_sustained_peak": (tfs / peaks["bf16_tflops_sustained"] / (0.5 if a.mode == "tf32" else 1.0))
+                       ("; tf32 runs at half the bf16 rate, so frac <= 0.5 in this mode" if a.mode == "tf32" else "") +
+                       ("; f16x3 spends 3 MMAs per multiply-add, so frac <= 1/3 in this mode" if a.mode == "f16x3" else ""),
+        # the same kernel against the rate of ITS instruction kind, measured in this run (cuBLAS through torch.matmul)
+        "mma_tflops": mma_tfs, "mma_per_flop": MMA_FACTOR[a.mode],
+        "peak_for_this_dtype": measured_peak,
+        "frac_of_dtype_peak": (mma_tfs / measured_peak["tflops"]) if measured_peak else None,
+        "frac_of_sustained_peak": (mma_tfs / peaks["bf16_tflops_sustained"] / (0.5 if a.mode == "tf32" else 1.0))
                                   if peaks.get("bf16_tflops_sustained") else None,
         "flop_per_launch": dom["work"] / max(1, dom["launches"]), "ms_per_launch": dom["ms"] / max(1, dom["launches"]),
         "launches": dom["launches"], "share_of_step": dom["ms"] / all_ms if all_ms else None,
@@ -428,15 +515,18 @@ def run_gpu(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": DTYPE_NAME[a.mode], "data": "synthetic",
-        "config": {"workload": workload_name(a), "scale": a.scale, "frames_per_gpu": B, "height": H, "width": W,
-                   "mode": a.mode, "weights": "synthetic seed 0 (reference init, output.weight x0.002)",
-                   "sharding": "independent frames per rank, no data-path collective",
-                   "l2": "256 MiB buffer written between timed steps (L2 flush, outside the event window)",
-                   "passes": f"device-timed, instrumented, blocking host calls, streaming host calls; {IDLE_S} s idle before each"},
+        "config": config_dict(a),
+        "timing": {"l2": "256 MiB buffer written between timed steps (L2 flush, outside the event window)",
+                   "passes": f"device-timed, instrumented, blocking host calls, streaming host calls, drop-in calls; "
+                             f"{IDLE_S} s idle before each"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * P * 4, "d2h_bytes_per_step": P * 4,
-                "api": "Engine.stream_host -> codon_forward_host_submit / _wait (pinned host fp32 frames in, pinned host fp32 "
-                       "depth out, every step; one call submitted ahead so that its H2D copy and the previous call's D2H copy "
-                       "run under the current call's kernels)",
+                "api": f"codon_b200.CODON_x{a.scale}.CODONNet.forward, called as the reference driver calls its model "
+                       "(CODON_X4/test.py:122-128): pinned host fp32 frames -> .to(cuda) -> model(x, y) -> copy back to pinned "
+                       "host memory -> synchronise, every step",
+                "module_overhead_us": key_us,
+                "streaming": {"value": world * P * steps / 1e6 / e2e_s, "unit": UNIT,
+                              "api": "Engine.stream_host -> codon_forward_host_submit / _wait (one call submitted ahead: its H2D "
+                                     "copy and the previous call's D2H copy run under the current call's kernels)"},
                 "blocking_call": {"value": world * P * steps / 1e6 / e2e_blocking_s, "unit": UNIT,
                                   "api": "Engine.forward_host -> codon_forward_host (copy in, forward, copy out, synchronise; "
                                          "nothing overlapped)"}},
@@ -448,7 +538,7 @@ def run_gpu(a):
         if not a.no_variants:
             variants = {}
             outs = {a.mode: out.clone()}
-            for m in ("fp32", "tf32", "fp16", "bf16"):
+            for m in ("fp32", "tf32", "f16x3", "fp16", "bf16"):
                 if m == a.mode:
                     continue
                 e2 = E.Engine(a.scale, m, local)
@@ -475,13 +565,13 @@ def run_gpu(a):
                 variants[a.mode + "+cuda_graph"] = {"value": P * steps / 1e6 / (gms / 1e3), "unit": UNIT, "ms_per_step": gms / steps}
             except Exception as exc:   # noqa: BLE001 - a variant, never the headline
                 variants[a.mode + "+cuda_graph"] = {"error": str(exc)[:200]}
-            line["variants"] = variants
+            line["roofline"]["variants"] = variants      # (under roofline: the driver's record keeps this object whole)
         else:
             outs = {a.mode: out.clone()}
         # ---- CPU baseline (oracle) on a bounded sample + parity of the GPU result against it --------
         if not a.no_cpu_baseline:
-            mps, desc, cores, ref, rows, _ = cpu_forward_sample(a.scale, H, W, 20.0, 1, 1)
-            line["cpu_baseline"] = {"value": mps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+            mps, desc, cores, ref, rows, _, kind = cpu_forward_sample(a.scale, H, W, 20.0, 1, 1)
+            line["cpu_baseline"] = {"value": mps, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
             # The sample is the top `rows` rows; the receptive field is 47 px and the CAC
             # pooling is global, so compare the GPU forward of the SAME cropped input.
             xs, ys = x[:1, :, :rows].contiguous(), y[:1, :, :rows].contiguous()
@@ -493,8 +583,10 @@ def run_gpu(a):
                 torch.cuda.synchronize()
                 par[m] = float((o.cpu() - ref).abs().max())
                 e2.close()
-            line["parity"] = {"max_abs_err_vs_cpu_oracle": par, "tolerance_fp32_mode": 1e-3,
-                              "input": f"top {rows} rows of frame 0"}
+            # (under config: the driver's record keeps this object whole)
+            line["config"]["parity_max_abs_vs_cpu_reference"] = par
+            line["config"]["parity_note"] = (f"max |GPU - CPU {kind} fp32 forward| on the top {rows} rows of frame 0; north_star "
+                                             "tolerance for the fp32 parity mode: 1e-3")
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

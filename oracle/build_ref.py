@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Recipe for oracle/_ref/: the reference's OWN model classes, taken from where they lie under /root/reference.
+
+TEST / BENCH INFRASTRUCTURE ONLY.  The reference implementation of the hot path is three small Python files per
+scale (CODON_x4.py / CODON_x16.py, CAC_module.py, attention/ResCBAM.py).  `build()` copies exactly those files into
+oracle/_ref/CODON_X{4,8,16}/ -- a build output: git-ignored, never committed, but shipped to the GPU box with the
+repository snapshot like the built .so -- so that `bench.py --impl reference` and the `cpu_baseline` leg can time the
+UNMODIFIED reference classes on the box's host cores (kind "reference") instead of the functional restatement in
+oracle/codon_oracle.py (kind "port", the fallback when oracle/_ref is absent).  Nothing under codon_b200/ imports it.
+
+  python oracle/build_ref.py          # needs /root/reference (or $CODON_REFERENCE); run by __graft_entry__.build()
+"""
+import importlib
+import os
+import shutil
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_OUT = os.path.join(HERE, "_ref")
+FILES = {
+    "CODON_X4": ["CODON_x4.py", "CAC_module.py", os.path.join("attention", "ResCBAM.py")],
+    "CODON_X8": ["CODON_x8.py", "CAC_module.py", os.path.join("attention", "ResCBAM.py")],
+    "CODON_X16": ["CODON_x16.py", "CAC_module.py"],
+}
+
+
+def build(reference_root=None) -> bool:
+    """Copies the reference's model files into oracle/_ref/.  Returns False (and leaves any earlier copy alone) when
+    the reference checkout is not present -- e.g. on the GPU box, which only uses the prebuilt copy."""
+    root = reference_root or os.environ.get("CODON_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(root, "CODON_X4")):
+        return False
+    for sub, files in FILES.items():
+        for f in files:
+            dst = os.path.join(REF_OUT, sub, f)
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(os.path.join(root, sub, f), dst)
+    return True
+
+
+def available() -> bool:
+    return all(os.path.exists(os.path.join(REF_OUT, sub, f)) for sub, files in FILES.items() for f in files)
+
+
+def load_model_class(scale: int):
+    """The reference's `CODONNet` class for a scale, imported from oracle/_ref (None if that was never built).
+    The three directories reuse module names (CAC_module, attention), so they are purged between imports."""
+    if not available():
+        return None
+    for m in ("CAC_module", "attention", "attention.ResCBAM", "CODON_x4", "CODON_x8", "CODON_x16"):
+        sys.modules.pop(m, None)
+    d = os.path.join(REF_OUT, f"CODON_X{scale}")
+    sys.path.insert(0, d)
+    try:
+        return importlib.import_module(f"CODON_x{scale}").CODONNet
+    finally:
+        sys.path.remove(d)
+
+
+if __name__ == "__main__":
+    ok = build()
+    print("oracle/_ref built from the reference checkout" if ok else "reference checkout not found; oracle/_ref unchanged",
+          "| available:", available())

@@ -25,9 +25,18 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "hr_depth_megapixels_per_second" and d["unit"] == "MP/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
     assert d["vs_baseline"] is None and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the reference's own classes when oracle/_ref has been built (oracle/build_ref.py), the oracle port otherwise
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "CODON_X4", "CODON_x4.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    # both arms print the same config object for the same command line (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+    import argparse
+    a = argparse.Namespace(scale=4, frames=1, height=32, width=48, mode="tf32")
+    assert d["config"] == bench.config_dict(a)
 
 
 def test_reference_arm_other_ranks_exit_quietly():
