@@ -151,6 +151,17 @@ int fail(codon_ctx* ctx, int code, const char* fmt, ...) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Kernel-variant switches for perf experiments (CODON_TC_2CTA, _2CTA_ALL, _FUSE, _CSTAT, _NACC_CONV, _NACC_PAIR) exist
+// only in builds with -DCODON_TC_EXPERIMENT; the product library takes every decision from the frame geometry.
+#ifdef CODON_TC_EXPERIMENT
+int exp_knob(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#else
+inline int exp_knob(const char*, int dflt) { return dflt; }
+#endif
+
 enum ProfCat { PC_CONV5_128 = 0, PC_PAIR = 1, PC_CONV3 = 2, PC_CONV1 = 3, PC_EDGE = 4, PC_CAC_STATS = 5, PC_CAC_MLP = 6, PC_CAC_APPLY = 7 };
 const char* const kProfNames[8] = {"conv5x5_128to128", "pair_3x3_5x5_64to128", "conv3x3", "conv1x1_128to64", "edge_1to64_64to1",
                                    "cac_stats", "cac_mlp", "cac_apply"};
@@ -172,6 +183,22 @@ struct ProfScope {
   ~ProfScope() { if (b) cudaEventRecord(b, st); }
 };
 
+int pick_nacc(int B, int H, int W, int njobs, int prefer, const char* env);
+int use_two_cta(int B, int H, int W, int nacc);
+
+// True when every 5x5 128->128 + 1x1 pair of the forward runs as the fused cluster kernel for this geometry (the
+// decisions of Runner::conv5_fused for the two-job CAC stages and the one-job fusion stages): the 128-channel
+// intermediate then never exists in HBM and the R2 region only has to hold the 128-channel encoder scratch.
+bool fused_everywhere(const codon_ctx* ctx, int B, int H, int W) {
+  if (ctx->mode == CODON_MODE_FP32 || !exp_knob("CODON_TC_FUSE", 1)) return false;
+  if (ctx->mode == CODON_MODE_F16X3) return true;
+  for (int njobs = 1; njobs <= 2; ++njobs) {
+    const int nacc = pick_nacc(B, H, W, njobs, 2, "CODON_TC_NACC_CONV");
+    if (nacc > 2 || !use_two_cta(B, H, W, nacc)) return false;
+  }
+  return true;
+}
+
 Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W, int part_chunks = 0) {
   Buffers b;
   const size_t P = (size_t)B * H * W, e = act_bytes(ctx->act);
@@ -180,7 +207,9 @@ Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W, int part_chunks 
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   b.xf = take(P * 4); b.yf = take(P * 4); b.of32 = take(P * 4);
   b.E = take(P * 128 * e); b.F = take(P * 128 * e);
-  b.MS = take(P * 256 * e); b.R2 = take(P * 256 * e);
+  // R2: conv3 / conv6 outputs of the un-fused path (2 x 128 channels); with the fused kernels only its first 128
+  // channels are used (scratch of the encoder's first layer)
+  b.MS = take(P * 256 * e); b.R2 = take(P * (fused_everywhere(ctx, B, H, W) ? 128 : 256) * e);
   b.FUSE = take(P * 64 * e); b.OF = take(P * 64 * e);
   b.pooled = take(P * 2 * 4 * 4);   // (max, mean) map, or 2 / 4 (max, sum) partial maps from the 1x1 epilogues
   b.chunks = cac_stats_chunks(B, H, W);
@@ -253,10 +282,10 @@ int get_tmap(codon_ctx* ctx, const void* base, int C, int box_w, int box_h, int 
 // layer class when the frame is large enough: 2 for the 5x5 layers in cluster mode (two TMEM buffers of
 // 2 accumulators -> the epilogue of a tile overlaps the MMAs of the next one), 4 for the HBM-bound
 // 1x1 / 3x3 layers (fewer, larger TMA boxes).  Small frames step down until there are >= 2 waves.
-int pick_nacc(int B, int H, int W, int njobs, int prefer, const char* env = nullptr) {
+int pick_nacc(int B, int H, int W, int njobs, int prefer, const char* env) {
   if (env) {                      // perf experiments: CODON_TC_NACC_PAIR / CODON_TC_NACC_CONV
-    const char* e = getenv(env);
-    if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) return atoi(e);
+    const int v = exp_knob(env, 0);
+    if (v == 1 || v == 2 || v == 4) return v;
   }
   for (int nacc = prefer; nacc > 1; nacc >>= 1) {
     const long tiles = (long)B * cdiv(W, tc_tile_w(nacc)) * cdiv(H, tc_tile_h(nacc)) * njobs;
@@ -267,8 +296,7 @@ int pick_nacc(int B, int H, int W, int njobs, int prefer, const char* env = null
 
 // The cluster-of-2 kernel pays off once a job has at least a couple of waves of tile pairs.
 int use_two_cta(int B, int H, int W, int nacc) {
-  static int env = -2;
-  if (env == -2) { const char* e = getenv("CODON_TC_2CTA"); env = e ? atoi(e) : -1; }
+  const int env = exp_knob("CODON_TC_2CTA", -1);
   if (env == 0 || env == 1) return env;
   const long tiles = (long)B * cdiv(W, tc_tile_w(nacc)) * cdiv(H, tc_tile_h(nacc));
   return tiles >= 148 ? 1 : 0;
@@ -335,8 +363,7 @@ struct Runner {
     }
     // the HBM-bound 1x1 / 3x3 layers measured slower in cluster mode; the 5x5 layers gain 15-20 %
     {
-      static int all = -1;
-      if (all < 0) { const char* e = getenv("CODON_TC_2CTA_ALL"); all = e ? atoi(e) : 0; }
+      const int all = exp_knob("CODON_TC_2CTA_ALL", 0);
       // cluster mode: the 5x5 layers (+15-20 %) and, with one patch per slab, the 3x3 layers (+30 %); the
       // stand-alone 1x1 (fallback path only) stays single-CTA: its epilogue emits the ChannelPool partials
       L.two_cta = (ks == 5 || ks == 3 || (all && !jobs[0].has_pool)) ? use_two_cta(B, Hdec, W, L.nacc) : 0;
@@ -360,8 +387,7 @@ struct Runner {
                     size_t res2; int res2_stride, res2_off; bool has_res; size_t pool; bool has_pool;
                     size_t cstat = 0; bool has_cstat = false; };
   int conv5_fused(size_t in, const FusedJob* jobs, int njobs) {
-    static int env = -2;
-    if (env == -2) { const char* e = getenv("CODON_TC_FUSE"); env = e ? atoi(e) : 1; }
+    const int env = exp_knob("CODON_TC_FUSE", 1);
     if (ctx->mode == CODON_MODE_FP32 || !env) return 1;
     const bool split = ctx->mode == CODON_MODE_F16X3;
     // split-fp16 operands: one accumulator per tile (four patch stages + the two-plane Y tile fill shared memory),
@@ -373,7 +399,6 @@ struct Runner {
     L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = 1; L.out_act = ctx->act;
     L.nacc = nacc; L.two_cta = 1; L.fuse = 1; L.pool_stride = px;
     L.y16_operand = ctx->mode == CODON_MODE_BF16 ? TC_BF16 : TC_F16;
-    if (split && !env) return fail(ctx, CODON_ERR_STATE, "f16x3 mode needs the fused 5x5 + 1x1 kernel (CODON_TC_FUSE=0 set)");
     const CUtensorMap* tm[2] = {nullptr, nullptr};
     for (int i = 0; i < njobs; ++i) {
       const TcLayer& l = ctx->w_tc.at(jobs[i].w5);
@@ -502,8 +527,7 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     {
       Runner::FusedJob fj[2] = {{"conv3", "confuse", 0, bf.F, 128, 0, 0, 0, 0, false, bf.pooled, true},
                                 {"conv6", "confuse_c", half, bf.F, 128, 64, 0, 0, 0, false, bf.pooled + 2 * pmap, true}};
-      static int use_cstat = -1;   // CODON_TC_CSTAT=0: perf experiments, stand-alone statistics pass instead
-      if (use_cstat < 0) { const char* e = getenv("CODON_TC_CSTAT"); use_cstat = e ? atoi(e) : 1; }
+      const int use_cstat = exp_knob("CODON_TC_CSTAT", 1);   // 0: perf experiments, stand-alone statistics pass instead
       if (!hook && use_cstat) {   // the epilogue also leaves the per-cell channel partials of the global pools (not in band mode)
         fj[0].cstat = bf.cstat; fj[0].has_cstat = true;
         fj[1].cstat = bf.cstat + bf.cstat_half; fj[1].has_cstat = true;

@@ -52,8 +52,9 @@ constexpr int kThreads = 320;                  // warp 0 producer, 1 MMA, 2-9 ep
 constexpr int kThreads2 = 352;
 constexpr int kWarpA = 8, kWarpMma = 9, kWarpB = 10;
 constexpr int kB2MaxStages = 9;                // barrier slots reserved for the weight ring of the cluster kernel
-// Perf-experiment knobs of the cluster kernel (CODON_TC_DEBUG bits, cycle accounting) exist only in builds with
-// -DCODON_TC_EXPERIMENT: the MMA issue loop is latency-bound, every extra instruction in it costs throughput.
+// Perf-experiment knobs of the convolution kernels (CODON_TC_DEBUG bits, cycle accounting, CODON_TC_PDL) exist only in
+// builds with -DCODON_TC_EXPERIMENT: the MMA issue loop is latency-bound, every extra instruction in it costs
+// throughput, and a product library does not read the environment.
 #ifdef CODON_TC_EXPERIMENT
 #define TC2_DBG(p, bit) (((p).debug & (bit)) != 0)
 #else
@@ -363,7 +364,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         const uint8_t* wslab = job.w + (size_t)s * p.slab_bytes;
         mbar_wait(bar_patch_empty + 8 * ps, pph ^ 1);
         if (elect_one()) {
-          if (p.debug & 4) mbar_arrive(bar_patch_full + 8 * ps);
+          if (TC2_DBG(p, 4)) mbar_arrive(bar_patch_full + 8 * ps);
           else {
             mbar_expect_tx(bar_patch_full + 8 * ps, p.patch_tx);
             tma_load_4d(s_patch + ps * p.patch_stage, tl.job ? &tmap1 : &tmap0, bar_patch_full + 8 * ps,
@@ -377,7 +378,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
             if (elect_one()) {
               const uint32_t bytes = p.b_bytes[dxi][dyi];
-              if (p.debug & 2) mbar_arrive(bar_b_full + 8 * bs);
+              if (TC2_DBG(p, 2)) mbar_arrive(bar_b_full + 8 * bs);
               else {
                 mbar_expect_tx(bar_b_full + 8 * bs, bytes);
                 bulk_load(s_b + bs * kBStageBytes, wslab + p.b_off[dxi][dyi], bytes, bar_b_full + 8 * bs);
@@ -406,11 +407,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
       const uint32_t d_base = tmem_base + (uint32_t)(buf * NACC * p.n_cols);
       uint32_t acc0 = 0;                        // 0 only for the very first MMA group of the tile
       for (int s = 0; s < p.nslab; ++s) {
-        if (!(p.debug & 16)) mbar_wait(bar_patch_full + 8 * ps, pph);
+        if (!TC2_DBG(p, 16)) mbar_wait(bar_patch_full + 8 * ps, pph);
         const uint32_t patch = s_patch + ps * p.patch_stage;
         for (int dxi = 0; dxi < p.ndx; ++dxi) {
           for (int dyi = 0; dyi < p.ndy; ++dyi) {
-            if (!(p.debug & 16)) mbar_wait(bar_b_full + 8 * bs, bph);
+            if (!TC2_DBG(p, 16)) mbar_wait(bar_b_full + 8 * bs, bph);
             tc_fence_after();
             const bool half = p.b_bytes[dxi][dyi] < (uint32_t)p.n_cols * 128u;
             const uint32_t idesc = half ? p.idesc_half : p.idesc_full;
@@ -420,7 +421,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             const uint64_t adesc0 = desc_a | desc_addr(patch + (uint32_t)p.dy_ord[dyi] * pitch + (uint32_t)p.dx_ord[dxi] * 128u);
             const bool last = (dxi == p.ndx - 1) && (dyi == p.ndy - 1);
             if (elect_one()) {
-              if (!(p.debug & 8)) {
+              if (!TC2_DBG(p, 8)) {
 #pragma unroll
                 for (int j = 0; j < NACC; ++j) {
                   if (j >= tl.nacc) break;
@@ -473,7 +474,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
       auto drain = [&](int i, const uint32_t (&r)[32]) {
         const int j = i >> cpa_sh, c0 = (i - (j << cpa_sh)) << 5;
         const int py = tl.y0 + (j / G::NAX) * kTcSubH + my, px = tl.x0 + (j % G::NAX) * kTcSubW + mx;
-        if ((py < p.H) && (px < p.W) && !(p.debug & 1)) {
+        if ((py < p.H) && (px < p.W) && !TC2_DBG(p, 1)) {
           const size_t pix = ((size_t)tl.n * p.H + py) * p.W + px;
           store_chunk<OutT>(r, job, pix, c0, p.relu != 0, OPERAND == TC_TF32);
           if (pool_mode) {
@@ -1504,7 +1505,9 @@ cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, i
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
+  // resolved once per process; one host thread per GPU may race here, hence the atomic (same value from every thread)
+  static std::atomic<EncodeFn> encode_cache{nullptr};
+  EncodeFn encode = encode_cache.load(std::memory_order_acquire);
   if (!encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -1512,6 +1515,7 @@ cudaError_t tc_encode_tmap(CUtensorMap* map, const void* base, int act, int C, i
     if (e != cudaSuccess) return e;
     if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
     encode = reinterpret_cast<EncodeFn>(fn);
+    encode_cache.store(encode, std::memory_order_release);
   }
   // split activations: the map sees the fp16 planes, a pixel of C containers = 2C fp16 ([64 hi | 64 lo] per slab)
   const int es = act == ACT_SPLIT16 ? 2 : act_bytes(act);
@@ -1623,8 +1627,12 @@ cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, con
     kp.main_tiles = split ? items - rem : items;
     kp.total_items = kp.main_tiles + (items - kp.main_tiles) * NACC;
   }
-  static int pdl = -1;         // CODON_TC_PDL=0: plain stream order (perf experiments)
-  if (pdl < 0) { const char* e = getenv("CODON_TC_PDL"); pdl = e ? atoi(e) : 1; }
+#ifdef CODON_TC_EXPERIMENT
+  const char* pdl_env = getenv("CODON_TC_PDL");          // 0: plain stream order (perf experiments)
+  const int pdl = pdl_env ? atoi(pdl_env) : 1;
+#else
+  const int pdl = 1;
+#endif
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1726,11 +1734,12 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, c
   kp.idesc_full = make_idesc(plan.operand, plan.n_cols, mma_m);
   kp.idesc_half = make_idesc(plan.operand, 64, mma_m);
   kp.relu = L.relu; kp.out_act = L.out_act; kp.is_tf32 = plan.operand == TC_TF32;
+#ifdef CODON_TC_EXPERIMENT
   {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("CODON_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-    kp.debug = dbg;
+    const char* e = getenv("CODON_TC_DEBUG");      // perf experiments only: results are garbage
+    kp.debug = e ? atoi(e) : 0;
   }
+#endif
   if (L.out_act != (plan.operand == TC_TF32 ? ACT_F32 : plan.operand == TC_BF16 ? ACT_BF16 : plan.operand == TC_SPLIT16 ? ACT_SPLIT16 : ACT_F16))
     return cudaErrorInvalidValue;   // activations are stored in the operand type
   if (plan.operand == TC_SPLIT16) {
