@@ -19,6 +19,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <map>
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <thread>
@@ -311,8 +312,10 @@ struct BandHook {
   int cy0 = 0, cy1 = 0;             // core rows [cy0, cy1) of the local image
   long global_hw = 0;               // pixels of the whole frame (the average pool divides by it)
   int chunk_off = 0, chunks_total = 0;   // this band's slot in / the size of the gathered partial buffer
+  int my_chunks = 0;                // chunk partials this band contributes (cell chunks on the fused path)
   virtual int halo(const size_t* off, const size_t* row_bytes, int n) = 0;
-  virtual int gather_parts(size_t part_off) = 0;
+  // all-gather of the bands' CAC chunk partials; optionally refreshes the halo rows of `n` buffers in the same exchange
+  virtual int gather_parts(size_t part_off, const size_t* off = nullptr, const size_t* row_bytes = nullptr, int n = 0) = 0;
   virtual ~BandHook() {}
 };
 
@@ -386,6 +389,7 @@ struct Runner {
   struct FusedJob { const char* w5; const char* w1; size_t in_add; size_t out2; int out2_stride, out2_off;
                     size_t res2; int res2_stride, res2_off; bool has_res; size_t pool; bool has_pool;
                     size_t cstat = 0; bool has_cstat = false; };
+  int core_y0 = 0, core_y1 = 0;      // row-band mode: the rows of the local image this GPU owns (cstat masking)
   int conv5_fused(size_t in, const FusedJob* jobs, int njobs) {
     const int env = exp_knob("CODON_TC_FUSE", 1);
     if (ctx->mode == CODON_MODE_FP32 || !env) return 1;
@@ -398,6 +402,7 @@ struct Runner {
     TcLaunch L;
     L.njobs = njobs; L.B = B; L.H = H; L.W = W; L.relu = 1; L.out_act = ctx->act;
     L.nacc = nacc; L.two_cta = 1; L.fuse = 1; L.pool_stride = px;
+    L.core_y0 = core_y0; L.core_y1 = core_y1;
     L.y16_operand = ctx->mode == CODON_MODE_BF16 ? TC_BF16 : TC_F16;
     const CUtensorMap* tm[2] = {nullptr, nullptr};
     for (int i = 0; i < njobs; ++i) {
@@ -482,6 +487,7 @@ struct Runner {
 int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int B, int H, int W, uint8_t* ws,
                 const Buffers& bf, cudaStream_t st, BandHook* hook = nullptr) {
   Runner r{ctx, ws, B, H, W, st, act_bytes(ctx->act), hook ? (int)(bf.px / (size_t)W) : H, bf.px};
+  if (hook) { r.core_y0 = hook->cy0; r.core_y1 = hook->cy1; }
   // band mode: refresh the halo rows of the buffers a layer wrote (no-op otherwise)
   auto halo = [&](std::initializer_list<size_t> offs, int channels_or_bytes, bool raw_bytes = false) -> int {
     if (!hook) return CODON_OK;
@@ -528,7 +534,7 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
       Runner::FusedJob fj[2] = {{"conv3", "confuse", 0, bf.F, 128, 0, 0, 0, 0, false, bf.pooled, true},
                                 {"conv6", "confuse_c", half, bf.F, 128, 64, 0, 0, 0, false, bf.pooled + 2 * pmap, true}};
       const int use_cstat = exp_knob("CODON_TC_CSTAT", 1);   // 0: perf experiments, stand-alone statistics pass instead
-      if (!hook && use_cstat) {   // the epilogue also leaves the per-cell channel partials of the global pools (not in band mode)
+      if (use_cstat) {   // the epilogue also leaves the per-cell channel partials of the global pools (band mode: core rows only)
         fj[0].cstat = bf.cstat; fj[0].has_cstat = true;
         fj[1].cstat = bf.cstat + bf.cstat_half; fj[1].has_cstat = true;
         fj_cstat = true;
@@ -580,17 +586,27 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
       const int core_h = hook->cy1 - hook->cy0;
       const size_t row0 = (size_t)hook->cy0 * W;
       float* my_part = part + (size_t)hook->chunk_off * 256;
-      const int my_chunks = cac_stats_chunks(1, core_h, W);
+      const int my_chunks = hook->my_chunks;
       if (tc_mode) {
-        CU_TRY(ctx, launch_cac_chan_stats(ws + bf.F + row0 * 128 * r.e, ctx->act, 1, core_h, W, my_part, my_chunks, st));
+        if (pool_parts == 4 && fj_cstat) {
+          // fused path: the epilogue's per-cell partials already count the core rows only
+          const int cells = cdiv(W, kTcSubW) * cdiv(H, kTcSubH);
+          if (my_chunks != cac_cell_chunks(cells)) return fail(ctx, CODON_ERR_STATE, "band mode: chunk plan does not match the fused path");
+          CU_TRY(ctx, launch_cac_cell_reduce(ws + bf.cstat, ws + bf.cstat + bf.cstat_half, 1, cells, my_part, my_chunks, st));
+        } else {
+          if (my_chunks != cac_stats_chunks(1, core_h, W)) return fail(ctx, CODON_ERR_STATE, "band mode: chunk plan does not match the stand-alone statistics pass");
+          CU_TRY(ctx, launch_cac_chan_stats(ws + bf.F + row0 * 128 * r.e, ctx->act, 1, core_h, W, my_part, my_chunks, st));
+        }
+        // the ChannelPool maps of the halo rows travel in the same exchange as the channel partials
         size_t o[4]; for (int k = 0; k < pool_parts; ++k) o[k] = bf.pooled + k * pmap;
         size_t rb[4] = {(size_t)W * 8, (size_t)W * 8, (size_t)W * 8, (size_t)W * 8};
-        if ((rc = hook->halo(o, rb, pool_parts))) return rc;
+        if ((rc = hook->gather_parts(bf.part, o, rb, pool_parts))) return rc;
       } else {
+        if (my_chunks != cac_stats_chunks(1, core_h, W)) return fail(ctx, CODON_ERR_STATE, "band mode: chunk plan does not match the statistics pass");
         CU_TRY(ctx, launch_cac_stats(ws + bf.F + row0 * 128 * r.e, ctx->act, 1, core_h, W, pooled + row0 * 2, my_part, my_chunks, st));
         if ((rc = halo({bf.pooled}, 8, true))) return rc;
+        if ((rc = hook->gather_parts(bf.part))) return rc;
       }
-      if ((rc = hook->gather_parts(bf.part))) return rc;
       CU_TRY(ctx, launch_cac_mlp(part, hook->chunks_total, 1, (int)hook->global_hw, ctx->cac_w1[s], ctx->cac_b1[s],
                                  ctx->cac_w2[s], ctx->cac_b2[s], sc, st));
     }
@@ -661,94 +677,158 @@ struct codon_group {
   std::vector<float*> din, dout;     // per GPU band inputs (x | y) and output
   std::vector<float*> pin;           // per GPU pinned staging (x | y | out)
   size_t cap_px = 0, ws_cap = 0;     // capacity (pixels of the tallest band, workspace bytes)
-  std::vector<std::vector<cudaEvent_t>> ev;   // [gpu][layer]
+  // Cross-GPU ordering without host rendezvous: flags[g] is an array of n counters in GPU g's memory; counter h is
+  // advanced by GPU h (a store through NVLink peer memory from h's exchange kernel, stream-ordered behind h's layer) and
+  // polled by GPU g's exchange kernel before it pulls rows from h.  seq_out[g][h] / seq_in[g][h] are the host-side
+  // mirrors of "how often g has signalled h" / "how many signals g has consumed from h"; every GPU enqueues the same
+  // exchange sequence, so the two sides count alike.
+  std::vector<uint32_t*> flags;
+  std::vector<std::vector<uint32_t>> seq_out, seq_in;
+  bool poisoned = false;             // a forward failed: streams are drained and the counters reset before the next one
   // geometry of the current forward
   int H = 0, W = 0;
   std::vector<int> r0, r1, mt, mb, hloc, chunk_off, chunks;
   int chunks_total = 0;
   Buffers bf;
-  // host-side rendezvous of the per-GPU threads
-  std::atomic<int> arrived{0}, generation{0};
   std::atomic<bool> failed{false};
   std::mutex err_mu;
   std::string err;
   double last_ms = 0.0;
 
-  bool barrier() {   // sense-reversing spin barrier; gives up as soon as any thread has failed
-    const int gen = generation.load(std::memory_order_acquire);
-    if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
-      arrived.store(0, std::memory_order_relaxed);
-      generation.fetch_add(1, std::memory_order_acq_rel);
-    } else {
-      while (generation.load(std::memory_order_acquire) == gen)
-        if (failed.load(std::memory_order_acquire)) return false;
-    }
-    return !failed.load(std::memory_order_acquire);
-  }
   void set_error(const std::string& m) {
-    std::lock_guard<std::mutex> lk(err_mu);
-    if (err.empty()) err = m;
-    failed.store(true, std::memory_order_release);
+    {
+      std::lock_guard<std::mutex> lk(err_mu);
+      if (err.empty()) err = m;
+    }
+    if (!failed.exchange(true, std::memory_order_acq_rel)) {
+      // release every exchange kernel that may be polling a counter this thread will never advance: all counters far
+      // ahead (cyclic comparison: 0x7f7f7f7f - want >= 0); the results of this forward are discarded anyway
+      for (int h = 0; h < n; ++h) {
+        if (!flags.empty() && flags[h] && cudaSetDevice(dev[h]) == cudaSuccess) cudaMemset(flags[h], 0x7F, (size_t)n * sizeof(uint32_t));
+      }
+    }
   }
 };
 
 namespace {
 
-constexpr int kGroupMaxLayers = 160;
+// One exchange = one kernel on the exchanging GPU's stream (stream-ordered behind the layer whose rows it publishes):
+//   1. signal: one thread stores this GPU's new counter value into each peer's flag array (system-scope fence first:
+//      the layer's results are visible before the counter is);
+//   2. wait:   every CTA polls this GPU's own flag array until each peer's counter has reached the expected value
+//      (acquire loads; a watchdog traps after ~2 s instead of hanging the GPU on a protocol bug);
+//   3. pull:   rows are copied out of peer memory with plain 16-byte loads over NVLink.
+// No DMA peer copies: the runtime may serialise those against other work of the source device, and every GPU must be
+// free to run ahead of its neighbours here; no host thread ever waits for another one.
+constexpr int kPullMax = 24, kPeerMax = 16;
+struct ExchangeArgs {
+  const uint8_t* src[kPullMax];
+  uint8_t* dst[kPullMax];
+  uint32_t bytes[kPullMax];      // multiples of 8 (rows of float2 maps, or of >= 64-channel pixels)
+  int nseg;
+  uint32_t* peer_flag[kPeerMax]; // where to publish my counter (peer memory)
+  uint32_t peer_val[kPeerMax];
+  const uint32_t* my_flag[kPeerMax];   // where the peers publish theirs (my memory)
+  uint32_t want[kPeerMax];
+  int npeer;
+  void add(const void* s, void* d, size_t n) { src[nseg] = static_cast<const uint8_t*>(s); dst[nseg] = static_cast<uint8_t*>(d); bytes[nseg] = (uint32_t)n; ++nseg; }
+};
+__global__ void __launch_bounds__(256) exchange_kernel(const ExchangeArgs a) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < a.npeer) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(a.peer_flag[threadIdx.x]) = a.peer_val[threadIdx.x];
+  }
+  if ((int)threadIdx.x < a.npeer) {
+    const uint32_t* f = a.my_flag[threadIdx.x];
+    const uint32_t want = a.want[threadIdx.x];
+    const long long t0 = clock64();
+    while (true) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int32_t)(v - want) >= 0) break;          // cyclic comparison
+      if (clock64() - t0 > 4000000000LL) {
+        printf("codon_group exchange: peer counter %d stuck at %u, expected %u\n", (int)threadIdx.x, v, want);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  for (int sgm = blockIdx.y; sgm < a.nseg; sgm += gridDim.y) {
+    const uint8_t* s = a.src[sgm];
+    uint8_t* d = a.dst[sgm];
+    const uint32_t n = a.bytes[sgm];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if ((((uintptr_t)s | (uintptr_t)d | n) & 15) == 0) {
+      for (uint32_t i = tid; i < (n >> 4); i += nth) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+    } else {
+      for (uint32_t i = tid; i < (n >> 3); i += nth) reinterpret_cast<uint2*>(d)[i] = reinterpret_cast<const uint2*>(s)[i];
+    }
+  }
+}
 
 struct GroupHook : BandHook {
-  codon_group* G; int g; int layer = 0;
+  codon_group* G; int g;
   GroupHook(codon_group* G_, int g_) : G(G_), g(g_) {}
 
-  // records "my layer is done", meets the other threads, then makes my stream wait for the given peers
-  int rendezvous(bool all_peers) {
-    if (layer >= kGroupMaxLayers) { G->set_error("codon_group: too many layers"); return CODON_ERR_STATE; }
-    cudaStream_t st = G->st[g];
-    if (cudaEventRecord(G->ev[g][layer], st) != cudaSuccess) { G->set_error("cudaEventRecord failed"); }
-    if (!G->barrier()) return CODON_ERR_CUDA;
-    for (int h = 0; h < G->n; ++h) {
-      if (h == g || (!all_peers && h != g - 1 && h != g + 1)) continue;
-      if (cudaStreamWaitEvent(st, G->ev[h][layer], 0) != cudaSuccess) G->set_error("cudaStreamWaitEvent failed");
+  // fills the signal / wait part for the given peers (advances the host-side mirrors of the counters) and launches
+  int launch(ExchangeArgs& a, const int* peers, int npeers) {
+    if (G->failed.load(std::memory_order_acquire)) return CODON_ERR_CUDA;
+    a.npeer = npeers;
+    for (int i = 0; i < npeers; ++i) {
+      const int h = peers[i];
+      a.peer_flag[i] = G->flags[h] + g;
+      a.peer_val[i] = ++G->seq_out[g][h];
+      a.my_flag[i] = G->flags[g] + h;
+      a.want[i] = ++G->seq_in[g][h];
     }
-    ++layer;
-    return G->failed.load() ? CODON_ERR_CUDA : CODON_OK;
+    uint32_t mx = 0;
+    for (int i = 0; i < a.nseg; ++i) mx = a.bytes[i] > mx ? a.bytes[i] : mx;
+    int bx = (int)(((mx >> 4) + 255) / 256);
+    if (bx > 32) bx = 32;
+    if (bx < 1) bx = 1;
+    exchange_kernel<<<dim3(bx, a.nseg > 0 ? a.nseg : 1), 256, 0, G->st[g]>>>(a);
+    if (cudaGetLastError() != cudaSuccess) { G->set_error("exchange_kernel launch failed"); return CODON_ERR_CUDA; }
+    return CODON_OK;
+  }
+
+  int add_halo(ExchangeArgs& a, const size_t* off, const size_t* rb, int nbuf) {
+    if (a.nseg + nbuf * 2 > kPullMax) { G->set_error("halo: too many buffers"); return CODON_ERR_STATE; }
+    for (int i = 0; i < nbuf; ++i)
+      if ((rb[i] & 7) || (off[i] & 7)) { G->set_error("halo rows are not 8-byte granular"); return CODON_ERR_STATE; }
+    auto add = [&](int h, size_t src_row, size_t dst_row) {
+      for (int i = 0; i < nbuf; ++i)
+        a.add(G->ws[h] + off[i] + src_row * rb[i], G->ws[g] + off[i] + dst_row * rb[i], (size_t)kBandHalo * rb[i]);
+    };
+    if (g > 0)            // my top halo rows <- the last core rows of the band above
+      add(g - 1, (size_t)(G->hloc[g - 1] - G->mb[g - 1] - kBandHalo), 0);
+    if (g < G->n - 1)     // my bottom halo rows <- the first core rows of the band below
+      add(g + 1, (size_t)G->mt[g + 1], (size_t)(G->hloc[g] - G->mb[g]));
+    return CODON_OK;
   }
 
   int halo(const size_t* off, const size_t* rb, int nbuf) override {
-    int rc = rendezvous(false);
-    if (rc) return rc;
-    cudaStream_t st = G->st[g];
-    for (int i = 0; i < nbuf; ++i) {
-      const size_t bytes = (size_t)kBandHalo * rb[i];
-      if (g > 0) {          // my top halo rows <- the last core rows of the band above
-        const int h = g - 1;
-        const uint8_t* src = G->ws[h] + off[i] + (size_t)(G->hloc[h] - G->mb[h] - kBandHalo) * rb[i];
-        if (cudaMemcpyPeerAsync(G->ws[g] + off[i], G->dev[g], src, G->dev[h], bytes, st) != cudaSuccess)
-          G->set_error("cudaMemcpyPeerAsync failed");
-      }
-      if (g < G->n - 1) {   // my bottom halo rows <- the first core rows of the band below
-        const int h = g + 1;
-        const uint8_t* src = G->ws[h] + off[i] + (size_t)G->mt[h] * rb[i];
-        uint8_t* dst = G->ws[g] + off[i] + (size_t)(G->hloc[g] - G->mb[g]) * rb[i];
-        if (cudaMemcpyPeerAsync(dst, G->dev[g], src, G->dev[h], bytes, st) != cudaSuccess)
-          G->set_error("cudaMemcpyPeerAsync failed");
-      }
-    }
-    return G->failed.load() ? CODON_ERR_CUDA : CODON_OK;
+    int peers[2], np = 0;
+    if (g > 0) peers[np++] = g - 1;
+    if (g < G->n - 1) peers[np++] = g + 1;
+    ExchangeArgs a;
+    a.nseg = 0;
+    if (add_halo(a, off, rb, nbuf)) return CODON_ERR_STATE;
+    return launch(a, peers, np);
   }
 
-  int gather_parts(size_t part_off) override {
-    int rc = rendezvous(true);
-    if (rc) return rc;
-    cudaStream_t st = G->st[g];
+  int gather_parts(size_t part_off, const size_t* off, const size_t* rb, int nbuf) override {
+    int peers[kPeerMax], np = 0;
+    ExchangeArgs a;
+    a.nseg = 0;
+    if (nbuf > 0 && add_halo(a, off, rb, nbuf)) return CODON_ERR_STATE;
+    if (a.nseg + G->n - 1 > kPullMax) { G->set_error("gather: too many segments"); return CODON_ERR_STATE; }
     for (int h = 0; h < G->n; ++h) {
       if (h == g) continue;
+      peers[np++] = h;
       const size_t o = part_off + (size_t)G->chunk_off[h] * 256 * sizeof(float);
-      const size_t bytes = (size_t)G->chunks[h] * 256 * sizeof(float);
-      if (cudaMemcpyPeerAsync(G->ws[g] + o, G->dev[g], G->ws[h] + o, G->dev[h], bytes, st) != cudaSuccess)
-        G->set_error("cudaMemcpyPeerAsync failed");
+      a.add(G->ws[h] + o, G->ws[g] + o, (size_t)G->chunks[h] * 256 * sizeof(float));
     }
-    return G->failed.load() ? CODON_ERR_CUDA : CODON_OK;
+    return launch(a, peers, np);
   }
 };
 
@@ -1330,11 +1410,13 @@ int codon_group_create(codon_group** out, codon_ctx** ctxs, int n) {
     for (int j = 0; j < i; ++j)
       if (ctxs[j]->device == ctxs[i]->device) return fail(nullptr, CODON_ERR_ARG, "codon_group_create: two contexts on device %d", ctxs[i]->device);
   }
+  if (n > 16) return fail(nullptr, CODON_ERR_ARG, "codon_group_create: at most 16 GPUs");
   codon_group* G = new codon_group();
   G->n = n;
   G->ctx.assign(ctxs, ctxs + n);
   G->dev.resize(n); G->st.resize(n); G->ws.assign(n, nullptr); G->din.assign(n, nullptr); G->dout.assign(n, nullptr);
-  G->pin.assign(n, nullptr); G->ev.resize(n);
+  G->pin.assign(n, nullptr); G->flags.assign(n, nullptr);
+  G->seq_out.assign(n, std::vector<uint32_t>(n, 0)); G->seq_in.assign(n, std::vector<uint32_t>(n, 0));
   G->r0.resize(n); G->r1.resize(n); G->mt.resize(n); G->mb.resize(n); G->hloc.resize(n); G->chunk_off.resize(n); G->chunks.resize(n);
   for (int g = 0; g < n; ++g) G->dev[g] = ctxs[g]->device;
   for (int g = 0; g < n; ++g) {
@@ -1349,8 +1431,10 @@ int codon_group_create(codon_group** out, codon_ctx** ctxs, int n) {
       cudaGetLastError();
     }
     CU_TRY(nullptr, cudaStreamCreateWithFlags(&G->st[g], cudaStreamNonBlocking));
-    G->ev[g].resize(kGroupMaxLayers);
-    for (auto& e : G->ev[g]) CU_TRY(nullptr, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    void* fl = nullptr;
+    CU_TRY(nullptr, cudaMalloc(&fl, (size_t)n * sizeof(uint32_t)));
+    CU_TRY(nullptr, cudaMemset(fl, 0, (size_t)n * sizeof(uint32_t)));
+    G->flags[g] = static_cast<uint32_t*>(fl);
   }
   *out = G;
   return CODON_OK;
@@ -1361,8 +1445,8 @@ void codon_group_destroy(codon_group* G) {
   group_free_buffers(G);
   for (int g = 0; g < G->n; ++g) {
     cudaSetDevice(G->dev[g]);
-    for (auto& e : G->ev[g]) cudaEventDestroy(e);
-    if (G->st[g]) cudaStreamDestroy(G->st[g]);
+    if (G->st[g]) { cudaStreamSynchronize(G->st[g]); cudaStreamDestroy(G->st[g]); }
+    if (G->flags[g]) cudaFree(G->flags[g]);
   }
   delete G;
 }
@@ -1376,16 +1460,35 @@ int codon_group_forward_host(codon_group* G, const float* depth, const float* gu
   const int n = G->n;
   if (H < n * 2 * kBandHalo) return fail(nullptr, CODON_ERR_ARG, "codon_group_forward_host: frame of %d rows is too small for %d bands", H, n);
   // ---- band geometry: rows split evenly; interior sides carry kBandHalo halo rows ----------------
+  if (G->poisoned) {
+    // a previous forward failed half-way: drain every stream, then restart the cross-GPU counters from zero
+    for (int g = 0; g < n; ++g) {
+      CU_TRY(nullptr, cudaSetDevice(G->dev[g]));
+      cudaDeviceSynchronize();
+      cudaGetLastError();
+      CU_TRY(nullptr, cudaMemset(G->flags[g], 0, (size_t)n * sizeof(uint32_t)));
+      std::fill(G->seq_out[g].begin(), G->seq_out[g].end(), 0u);
+      std::fill(G->seq_in[g].begin(), G->seq_in[g].end(), 0u);
+    }
+    G->poisoned = false;
+  }
   int hmax = 0;
   G->H = H; G->W = W;
-  G->chunks_total = 0;
   for (int g = 0; g < n; ++g) {
     G->r0[g] = (int)((long)H * g / n); G->r1[g] = (int)((long)H * (g + 1) / n);
     G->mt[g] = g > 0 ? kBandHalo : 0; G->mb[g] = g < n - 1 ? kBandHalo : 0;
     G->hloc[g] = G->r1[g] - G->r0[g] + G->mt[g] + G->mb[g];
     if (G->hloc[g] > hmax) hmax = G->hloc[g];
+  }
+  // CAC chunk partials per band: folded 8 x 16-pixel cells of the local image when the fused conv epilogue produces the
+  // statistics (tensor-core modes, every GPU takes that decision from the tallest band), 256-pixel chunks of the core
+  // rows otherwise
+  const bool fused_stats = fused_everywhere(G->ctx[0], 1, hmax, W) && exp_knob("CODON_TC_CSTAT", 1);
+  G->chunks_total = 0;
+  for (int g = 0; g < n; ++g) {
     G->chunk_off[g] = G->chunks_total;
-    G->chunks[g] = cac_stats_chunks(1, G->r1[g] - G->r0[g], W);
+    G->chunks[g] = fused_stats ? cac_cell_chunks(cdiv(W, kTcSubW) * cdiv(G->hloc[g], kTcSubH))
+                               : cac_stats_chunks(1, G->r1[g] - G->r0[g], W);
     G->chunks_total += G->chunks[g];
   }
   G->bf = plan_buffers(G->ctx[0], 1, hmax, W, G->chunks_total);
@@ -1402,7 +1505,7 @@ int codon_group_forward_host(codon_group* G, const float* depth, const float* gu
     }
     G->cap_px = px; G->ws_cap = G->bf.total;
   }
-  G->failed.store(false); G->arrived.store(0); G->err.clear();
+  G->failed.store(false); G->err.clear();
 
   auto worker = [&](int g) {
     codon_ctx* ctx = G->ctx[g];
@@ -1419,7 +1522,7 @@ int codon_group_forward_host(codon_group* G, const float* depth, const float* gu
     GroupHook hook(G, g);
     hook.cy0 = G->mt[g]; hook.cy1 = hl - G->mb[g];
     hook.global_hw = (long)H * W;
-    hook.chunk_off = G->chunk_off[g]; hook.chunks_total = G->chunks_total;
+    hook.chunk_off = G->chunk_off[g]; hook.chunks_total = G->chunks_total; hook.my_chunks = G->chunks[g];
     uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(G->ws[g]), 1024));
     ctx->launches = 0;
     int rc = run_forward(ctx, G->din[g], G->din[g] + px, G->dout[g], 1, hl, W, ws, G->bf, st, &hook);
@@ -1439,7 +1542,10 @@ int codon_group_forward_host(codon_group* G, const float* depth, const float* gu
   worker(0);
   for (auto& t : th) t.join();
   G->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  if (G->failed.load()) return fail(nullptr, CODON_ERR_CUDA, "codon_group_forward_host: %s", G->err.c_str());
+  if (G->failed.load()) {
+    G->poisoned = true;
+    return fail(nullptr, CODON_ERR_CUDA, "codon_group_forward_host: %s", G->err.c_str());
+  }
   return CODON_OK;
 }
 

@@ -80,6 +80,7 @@ struct TcKParams {
   int fuse_njobs;
   unsigned long long pool_stride;   // fused mode: pixels between the two half-channel pool maps of a job
   int cells_x, cells_y;             // fused mode: 8 x 16-pixel cells per frame (TcJob::cstat)
+  int core_y0, core_y1;             // fused mode: rows that count towards cstat (row-band mode; whole image otherwise)
   int debug;   // CODON_TC_DEBUG bits (perf experiments only; results are garbage): 1 no epilogue stores, 2 no B loads, 4 no A loads,
                // 8 no MMAs (1-CTA), 16 no waits (1-CTA), 32 no epilogue TMEM loads / Y staging (cluster kernel)
 };
@@ -1195,7 +1196,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             // differ in bit k exchange the half of the channels they do not keep (31 shuffles; lane l ends with channel
             // l).  Max: one warp-collective redux.sync.max.f32 per channel (CREDUX, uniform datapath) -- shuffles go
             // through the shared-memory crossbar, which the MMA operand reads already keep ~80 % busy.
-            const bool live = (py < p.H) && (px < p.W);
+            const bool live = (py < p.core_y1) && (py >= p.core_y0) && (px < p.W);   // core_y1 <= H
             float sv[32];
             float mv0 = -INFINITY;
 #pragma unroll
@@ -1756,6 +1757,7 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, c
       kp.fuse_njobs = L.njobs;
       kp.pool_stride = L.pool_stride ? L.pool_stride : (unsigned long long)L.B * L.H * L.W;
       kp.cells_x = cdiv(L.W, kTcSubW); kp.cells_y = cdiv(L.H, kTcSubH);
+      kp.core_y0 = L.core_y1 > 0 ? L.core_y0 : 0; kp.core_y1 = L.core_y1 > 0 ? (L.core_y1 < L.H ? L.core_y1 : L.H) : L.H;
       return launch_nacc2<1, TC_SPLIT16, true, TK_5X5>(tmap, tmapj1, b0, b1, *L.wmap[0], *L.wmap[L.njobs > 1 ? 1 : 0], kp, st);
     }
     if (plan.pair) {
@@ -1780,6 +1782,7 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmap, const CUtensorMap& tmapj1, c
       kp.fuse_njobs = L.njobs;
       kp.pool_stride = L.pool_stride ? L.pool_stride : (unsigned long long)L.B * L.H * L.W;
       kp.cells_x = cdiv(L.W, kTcSubW); kp.cells_y = cdiv(L.H, kTcSubH);
+      kp.core_y0 = L.core_y1 > 0 ? L.core_y0 : 0; kp.core_y1 = L.core_y1 > 0 ? (L.core_y1 < L.H ? L.core_y1 : L.H) : L.H;
       const CUtensorMap& w0 = *L.wmap[0];
       const CUtensorMap& w1 = *L.wmap[L.njobs > 1 ? 1 : 0];
       if (!plan_matches_kind<TK_5X5>(plan)) return cudaErrorInvalidValue;

@@ -85,6 +85,9 @@ struct TcLaunch {
   int out_act = 0;             // ActType of out / res
   int nacc = 4;                // accumulators (128-pixel sub-tiles) per CTA tile: 1, 2 or 4
   size_t pool_stride = 0;      // fused mode: pixels between the two 32-channel-half pool maps of a job (0: B*H*W)
+  // fused mode, row-band multi-GPU forward: only image rows [core_y0, core_y1) count towards TcJob::cstat (the other
+  // rows are halo rows owned by a neighbouring band); core_y1 <= 0 means all rows
+  int core_y0 = 0, core_y1 = 0;
   int fuse = 0;                // 1 (two_cta, 5x5 128->128 only): the following 1x1 128->64 convolution runs as a second
                                // GEMM out of TMEM inside the same kernel (job.out2 / res2, wmap); job.out is not written
   int y16_operand = TC_BF16;   // 16-bit type of the staged ReLU output and of the 1x1 weights (TC_F16 / TC_BF16)

@@ -242,11 +242,13 @@ def run_big(scale, seed, shape, name, frame_seed, frames=(0,), with_fp64=True):
             for k, v in big_summary(out32[f, 0]).items():
                 rec[f"f{f}_fp32_{k}"] = v
         if with_fp64:
-            out64 = net.double()(x.double(), y.double()).numpy()
+            # frame by frame (frames are independent: CAC pools per sample): a whole fp64 batch does not fit in memory
+            net64 = net.double()
             for f in frames:
-                for k, v in big_summary(out64[f, 0]).items():
+                out64 = net64(x[f:f + 1].double(), y[f:f + 1].double()).numpy()
+                for k, v in big_summary(out64[0, 0]).items():
                     rec[f"f{f}_fp64_{k}"] = v
-            print(f"big_{name}: fp32-vs-fp64 max-abs {np.abs(out32 - out64).max():.2e}", flush=True)
+                print(f"big_{name}: frame {f} fp32-vs-fp64 max-abs {np.abs(out32[f:f + 1] - out64).max():.2e}", flush=True)
     np.savez_compressed(os.path.join(GOLD, f"big_{name}.npz"), **rec)
     print(f"big_{name}: x{scale} seed {seed} {shape} done", flush=True)
 
@@ -285,10 +287,18 @@ if __name__ == "__main__":
         write_c_case("fwd_x4_s0_b2_48x64.npz", "c_case_x4_s0_b2_48x64.bin")
     if what in ("all", "images"):
         run_image_parity_refs()
+    if what.startswith("big:"):       # one shape: big:x8 | big:720 | big:1080
+        which = what.split(":")[1]
+        if which == "x8":
+            run_big(8, 1, (8, 480, 640), "x8_b8_640x480", 2000, frames=(0, 7))
+        elif which == "720":
+            run_big(4, 2, (1, 720, 1280), "x4_1280x720", 3000)
+        elif which == "1080":
+            run_big(16, 0, (1, 1080, 1920), "x16_1920x1080", 4000, with_fp64=False)
     if what in ("all", "big"):
         # BASELINE.json configs[1..4]: x4 640x480; x8 batch of 8 x 640x480 (one GPU's shard of the 64);
         # x16 1920x1080; 1280x720 (x4 here; configs[4] cycles the scales)
         run_big(4, 0, (1, 480, 640), "x4_640x480", 1234)
         run_big(8, 1, (8, 480, 640), "x8_b8_640x480", 2000, frames=(0, 7))
         run_big(4, 2, (1, 720, 1280), "x4_1280x720", 3000)
-        run_big(16, 0, (1, 1080, 1920), "x16_1920x1080", 4000)
+        run_big(16, 0, (1, 1080, 1920), "x16_1920x1080", 4000, with_fp64=False)   # fp64 at 1080p needs > 60 GB
