@@ -1307,9 +1307,12 @@ int codon_cac_channel(const float* x, int B, int C, int H, int W, const float* w
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   float* tmp = nullptr;
   CU_TRY(nullptr, cudaMallocAsync(reinterpret_cast<void**>(&tmp), (size_t)4 * B * C * sizeof(float), st));
-  CU_TRY(nullptr, launch_nchw_channel_stats(x, B, C, H * W, pool_mask, tmp, st));
-  CU_TRY(nullptr, launch_gate_mlp(tmp, B, C, pool_mask, w1, b1, w2, b2, hidden, c_out, scale, st));
-  CU_TRY(nullptr, cudaFreeAsync(tmp, st));
+  // the temporary is released on every path (stream-ordered free), also when a launch fails
+  cudaError_t e = launch_nchw_channel_stats(x, B, C, H * W, pool_mask, tmp, st);
+  if (e == cudaSuccess) e = launch_gate_mlp(tmp, B, C, pool_mask, w1, b1, w2, b2, hidden, c_out, scale, st);
+  const cudaError_t ef = cudaFreeAsync(tmp, st);
+  if (e != cudaSuccess) return fail(nullptr, CODON_ERR_CUDA, "codon_cac_channel: %s", cudaGetErrorString(e));
+  CU_TRY(nullptr, ef);
   return CODON_OK;
 }
 
@@ -1319,9 +1322,11 @@ int codon_cac_spatial(const float* x, int B, int C, int H, int W, const float* w
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   float* tmp = pooled;
   if (!tmp) CU_TRY(nullptr, cudaMallocAsync(reinterpret_cast<void**>(&tmp), (size_t)2 * B * H * W * sizeof(float), st));
-  CU_TRY(nullptr, launch_nchw_channel_pool(x, B, C, H * W, tmp, st));
-  CU_TRY(nullptr, launch_nchw_spatial_scale(tmp, w, B, H, W, scale, st));
-  if (!pooled) CU_TRY(nullptr, cudaFreeAsync(tmp, st));
+  cudaError_t e = launch_nchw_channel_pool(x, B, C, H * W, tmp, st);
+  if (e == cudaSuccess) e = launch_nchw_spatial_scale(tmp, w, B, H, W, scale, st);
+  const cudaError_t ef = pooled ? cudaSuccess : cudaFreeAsync(tmp, st);
+  if (e != cudaSuccess) return fail(nullptr, CODON_ERR_CUDA, "codon_cac_spatial: %s", cudaGetErrorString(e));
+  CU_TRY(nullptr, ef);
   return CODON_OK;
 }
 

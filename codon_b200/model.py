@@ -111,6 +111,19 @@ class CODONNetBase(nn.Module):
             self._plist = list(self.parameters())
         return (self._wver, tuple((p.data_ptr(), p._version) for p in self._plist))
 
+    def _current_weights(self) -> Dict[str, torch.Tensor]:
+        """name -> tensor of this module tree.  A DataParallel replica keeps its broadcast copies in
+        ``_former_parameters`` (its ``_parameters`` are empty, so ``state_dict()`` would be too)."""
+        if not getattr(self, "_is_replica", False):
+            return dict(self.state_dict())
+        out: Dict[str, torch.Tensor] = {}
+        for prefix, m in self.named_modules():
+            held = dict(getattr(m, "_former_parameters", None) or {})
+            held.update({k: v for k, v in m._parameters.items() if v is not None})
+            for k, v in held.items():
+                out[f"{prefix}.{k}" if prefix else k] = v
+        return out
+
     def engine(self, device: torch.device) -> _eng.Engine:
         """The (cached) engine for this device/mode, with the current parameter values uploaded."""
         mode = self.mode
@@ -122,7 +135,7 @@ class CODONNetBase(nn.Module):
         with self._engine_lock:
             hit = self._engines.get(key)
             eng = hit[0] if hit is not None else _eng.Engine(self.SCALE, mode, key[0])
-            eng.load_state_dict({k: v for k, v in self.state_dict().items()})
+            eng.load_state_dict(self._current_weights())
             if wkey[1] is None and hit is not None:
                 wkey = (wkey[0], hit[1][1])
             self._engines[key] = (eng, wkey)

@@ -297,6 +297,56 @@ def test_full_size_linearity_property_free_checks():
         assert torch.equal(net(xc, yc), xc)
 
 
+def test_huge_activations_saturate_instead_of_overflowing():
+    """The fused 5x5 -> ReLU -> 1x1 kernel stages the 128-channel intermediate in fp16 (tf32 / fp16 / f16x3 modes).  With
+    weights scaled so that post-ReLU activations exceed the fp16 range (65504) the staging saturates: the output stays
+    finite (the reference's own .half() GPU path would produce inf / nan here).  fp32-storage modes keep tracking the
+    fp32 FFMA mode up to the saturation."""
+    sd = dict(orc.synthetic_state_dict(4, 0))
+    sd["conv_input.weight"] = sd["conv_input.weight"] * 1.0e6          # encoder outputs ~2e5 > 65504
+    sd["conv_input_c.weight"] = sd["conv_input_c.weight"] * 1.0e6
+    sd["output.weight"] = sd["output.weight"] * 1e-9
+    x, y = orc.synthetic_frames(1, 160, 240, 5)
+    outs = {}
+    for mode in ("fp32", "tf32", "f16x3"):
+        net = CODON_x4.CODONNet().eval().set_mode(mode)
+        net.load_state_dict(sd)
+        with torch.no_grad():
+            outs[mode] = net(x.cuda(), y.cuda())
+        eng = net.engine(torch.device("cuda", 0))
+        peak = float(eng.debug_tap("enc", 1, 160, 240).abs().max())
+        print(f"{mode}: encoder peak {peak:.3e}, output finite {bool(torch.isfinite(outs[mode]).all())}")
+        assert torch.isfinite(outs[mode]).all(), mode
+        if mode == "fp32":
+            assert peak > 65504.0            # the regime the test is about
+    assert float(eng.debug_tap("enc", 1, 160, 240).abs().max()) <= 2 * 65504.0      # split storage saturates (hi + lo)
+
+
+def test_dataparallel_wrapper_keeps_engines_and_weights():
+    """torch.nn.DataParallel(model) as in CODON_X16/test.py:52,132: the forward works through the wrapper on one GPU and,
+    when two are visible, through its replicas -- which share the master's engines: weights are uploaded once per device,
+    not once per forward (the weights generation of each engine stays put)."""
+    sd = orc.synthetic_state_dict(16, 2)
+    net = CODON_x16.CODONNet().eval().set_mode("bf16")
+    net.load_state_dict(sd)
+    ndev = min(torch.cuda.device_count(), 2)
+    x, y = orc.synthetic_frames(2 * ndev, 64, 80, 99)
+    with torch.no_grad():
+        # reference: the same per-GPU batches on one GPU (DataParallel scatters the batch in equal chunks; a frame's bits
+        # are batch-invariant as long as the batch takes the same kernel variants, which depend on the tile count)
+        per = x.shape[0] // ndev
+        ref = torch.cat([net(x[i:i + per].cuda(), y[i:i + per].cuda()).clone() for i in range(0, x.shape[0], per)])
+        dp = torch.nn.DataParallel(net, device_ids=list(range(ndev))).cuda()
+        assert set(dp.state_dict()) == {"module." + k for k in sd}
+        first = dp(x.cuda(), y.cuda()).clone()      # (.cuda() above went through _apply: one legitimate re-upload)
+        gens = {k: e.weights_generation for k, (e, _) in net._engines.items()}
+        outs = [dp(x.cuda(), y.cuda()).clone() for _ in range(3)]
+    for o in [first] + outs:
+        assert torch.equal(o.cpu(), ref.cpu())                     # frames are independent: same bits on any GPU
+    assert len(gens) == ndev, gens
+    assert {k: e.weights_generation for k, (e, _) in net._engines.items()} == gens     # no upload per forward
+
+
 def test_cuda_graph_replay_is_bit_exact():
     """The whole forward is capturable into a CUDA graph (no allocation, no sync inside codon_forward)."""
     sd = orc.synthetic_state_dict(4, 0)
@@ -312,6 +362,15 @@ def test_cuda_graph_replay_is_bit_exact():
         assert torch.equal(g(x.cuda(), y.cuda()), direct)
         assert torch.equal(g(x2.cuda(), y2.cuda()), direct2)
         assert torch.equal(g(x.cuda(), y.cuda()), direct)
+        # reloading weights keeps the graph usable: same device allocations, and the replay re-captures (per-layer
+        # constants such as the f16x3 weight scales live in the captured kernel parameters)
+        sd2 = orc.synthetic_state_dict(4, 1)
+        eng.load_state_dict(sd2)
+        with torch.no_grad():
+            want = eng.forward(x.cuda(), y.cuda()).clone()
+        assert not torch.equal(want, direct)
+        assert torch.equal(g(x.cuda(), y.cuda()), want)
+        eng.load_state_dict(sd)
 
 
 def test_1080p_x16_in_kernel_tiling_properties():
