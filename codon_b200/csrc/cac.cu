@@ -292,19 +292,22 @@ __global__ void __launch_bounds__(1024) cac_mlp_kernel(const float* __restrict__
   }
 }
 
-constexpr int kATH = 8, kATW = 32;   // apply tile: 256 pixels
+// apply tile: up to 8 x 32 pixels.  The tile HEIGHT is chosen per launch (4 .. 8 rows) so that the tile count comes close
+// to a whole number of waves of resident CTAs: at 640x480 x 1 frame, 8-row tiles are 1200 CTAs = 2.03 waves of 592 (the
+// kernel ran three waves' worth of time for two waves of work: 0.70 of the HBM peak), 6-row tiles are 1600 = 2.7 waves.
+constexpr int kATH = 8, kATW = 32;
 
 template <typename T>
 __global__ void __launch_bounds__(256, 4) cac_apply_kernel(T* __restrict__ F, const T* __restrict__ E,
                                                            const float* __restrict__ pooled,
                                                            const float* __restrict__ sc,
                                                            const float* __restrict__ ws, int H, int W,
-                                                        int tiles_x, int rnd_tf32, int pool_parts, size_t part_stride) {
+                                                        int tiles_x, int rnd_tf32, int pool_parts, size_t part_stride, int th) {
   constexpr int V = Act<T>::kVec, LPP = 128 / V, PH = kATH + 4, PW = kATW + 4;
   __shared__ float2 sp[PH][PW];
   __shared__ float sw[50], ssc[64], sss[kATH * kATW];
   const int b = blockIdx.y, t = threadIdx.x;
-  const int ty0 = (blockIdx.x / tiles_x) * kATH, tx0 = (blockIdx.x % tiles_x) * kATW;
+  const int ty0 = (blockIdx.x / tiles_x) * th, tx0 = (blockIdx.x % tiles_x) * kATW;   // th <= kATH rows per tile
   const size_t fb = (size_t)b * H * W;
   // The tile's F / E vectors do not depend on the gate: the first batch of kU + kU 16-byte loads is issued before
   // the pooled-halo staging and the 5x5 gate convolution, so HBM is busy while the CTA computes s_s (r01h: every
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(256, 4) cac_apply_kernel(T* __restrict__ F, co
     for (int u = 0; u < kU; ++u) {
       const int i = t + (bt * kU + u) * 256, g = i % LPP, px = i / LPP;
       const int gy = ty0 + px / kATW, gx = tx0 + px % kATW;
-      pix[u] = (gy < H && gx < W) ? gy * W + gx : -1;
+      pix[u] = (px < th * kATW && gy < H && gx < W) ? gy * W + gx : -1;
       if (pix[u] >= 0) {
         const size_t o = (fb + (size_t)pix[u]) * 128 + g * V;
         rf[u] = Act<T>::ld(F + o);
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(256, 4) cac_apply_kernel(T* __restrict__ F, co
   fetch(0);
   if (t < 50) sw[t] = ws[t];
   if (t >= 64 && t < 128) ssc[t - 64] = sc[b * 64 + t - 64];
-  for (int i = t; i < PH * PW; i += 256) {
+  for (int i = t; i < (th + 4) * PW; i += 256) {
     const int gy = ty0 + i / PW - 2, gx = tx0 + i % PW - 2;
     float2 v = make_float2(0.f, 0.f);
     if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(256, 4) cac_apply_kernel(T* __restrict__ F, co
     sp[i / PW][i % PW] = v;
   }
   __syncthreads();
-  {
+  if (t < th * kATW) {
     const int r = t / kATW, c = t % kATW;
     float q = 0.f;
 #pragma unroll
@@ -431,11 +434,21 @@ cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* poole
                              size_t part_stride) {
   const int tiles_x = cdiv(W, kATW);
   if (part_stride == 0) part_stride = (size_t)B * H * W;
-  dim3 grid(tiles_x * cdiv(H, kATH), B);
-  if (act == ACT_F32) cac_apply_kernel<float><<<grid, 256, 0, st>>>((float*)F, (const float*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride);
-  else if (act == ACT_BF16) cac_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)F, (const __nv_bfloat16*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride);
-  else if (act == ACT_SPLIT16) cac_apply_kernel<split16><<<grid, 256, 0, st>>>((split16*)F, (const split16*)E, pooled, sc, ws, H, W, tiles_x, 0, pool_parts, part_stride);
-  else cac_apply_kernel<__half><<<grid, 256, 0, st>>>((__half*)F, (const __half*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride);
+  // tile height: the one that needs the least (waves of 148 x 4 resident CTAs) x (rows per tile)
+  int th = kATH;
+  {
+    long best = -1;
+    for (int h = kATH; h >= 4; --h) {
+      const long tiles = (long)tiles_x * cdiv(H, h) * B;
+      const long cost = ((tiles + 591) / 592) * h;
+      if (best < 0 || cost < best) { best = cost; th = h; }
+    }
+  }
+  dim3 grid(tiles_x * cdiv(H, th), B);
+  if (act == ACT_F32) cac_apply_kernel<float><<<grid, 256, 0, st>>>((float*)F, (const float*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride, th);
+  else if (act == ACT_BF16) cac_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)F, (const __nv_bfloat16*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride, th);
+  else if (act == ACT_SPLIT16) cac_apply_kernel<split16><<<grid, 256, 0, st>>>((split16*)F, (const split16*)E, pooled, sc, ws, H, W, tiles_x, 0, pool_parts, part_stride, th);
+  else cac_apply_kernel<__half><<<grid, 256, 0, st>>>((__half*)F, (const __half*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride, th);
   return cudaGetLastError();
 }
 

@@ -104,9 +104,12 @@ enum TcKind : int { TK_3X3 = 0, TK_5X5 = 1, TK_PAIR = 2 };
 #ifndef CODON_SPLIT_TPC_5X5
 #define CODON_SPLIT_TPC_5X5 5
 #endif
-// split-fp16 mode: on the hi weight block, alternate the big / small accumulators K step by K step (+1 %)
-#ifndef CODON_SPLIT_INTERLEAVE
-#define CODON_SPLIT_INTERLEAVE 1
+// non-split kernels: taps issued per elect / fence / branch block (1 = one tap per block as in round 1; 2 = two taps,
+// i.e. two ring stages awaited and released per block -- the issue loop's bookkeeping limits the tensor pipe).
+// Same-session A/B on B200 (profiles/r02_ab_tap_group.txt): 5x5 128->128 fused +5.5 % (bf16: 1.62 -> 1.71 PFLOP/s),
+// +2.5 % (tf32); the 3x3 || 5x5 pair and the 3x3 layers do not move (pair tf32 -2 %), so only the 5x5 kind uses 2.
+#ifndef CODON_TC_TAP_GROUP
+#define CODON_TC_TAP_GROUP 0      // 0: per kernel kind (5x5: 2, others: 1)
 #endif
 template <int KIND> struct Taps {
   static constexpr int KS = KIND == TK_3X3 ? 3 : 5;
@@ -693,6 +696,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   constexpr int NU = SPLIT ? 2 * TP::NT : TP::NT;                // weight-ring uses per slab
   constexpr int kTPC = KIND == TK_3X3 ? CODON_SPLIT_TPC_3X3 : CODON_SPLIT_TPC_5X5;   // taps per accumulation chunk
   constexpr int kSplitBufs = 3;
+  constexpr int kTapGroup = CODON_TC_TAP_GROUP ? CODON_TC_TAP_GROUP : (KIND == TK_5X5 ? 2 : 1);
   static_assert(TP::NT % kTPC == 0, "chunks must tile the taps of a slab");
   static_assert(!SPLIT || NACC == 1, "split mode: one accumulator (big + small, double-buffered) per tile");
   constexpr uint32_t kPitch = (uint32_t)(G::TW + TP::KS - 1) * 128u;   // patch row pitch in bytes (== p.pw * 128)
@@ -927,89 +931,153 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           // stage and its barriers are immediates.  The phase test of the NEXT tap's weights is issued before this
           // tap's MMAs so that its latency hides behind their issue.
           bool ready = mbar_test(bar_b_full, par_even);
-          static_for<NU>([&](auto U) {
-            constexpr int u = decltype(U)::value;
-            constexpr int t = SPLIT ? u / 2 : u, plane = SPLIT ? (u & 1) : 0;
-            constexpr bool outer = TP::outer(t);
-            constexpr int st = u % NST;
-            constexpr uint32_t tap_off = ((uint32_t)TP::dy(t) * kPitch + (uint32_t)TP::dx(t) * 128u) >> 4;
-            // split mode: accumulation chunk = kTPC taps of this slab, in its own big / small accumulator pair
-            constexpr bool chunk_start = SPLIT && plane == 0 && (t % kTPC) == 0;
-            constexpr bool chunk_end = SPLIT && plane == 1 && (t % kTPC) == kTPC - 1;
-            if (chunk_start) {
-              buf = sbuf;
-              acquire_acc(buf, sbuf_par ^ 1u);
-              d_base = tmem_base + (uint32_t)buf * n_cols;
-              if (++sbuf == kSplitBufs) { sbuf = 0; sbuf_par ^= 1u; }
-              if (u == 0 && s == 0) {
-                // the tile's first small MMA overwrites the small accumulator: the previous tile's must have been read
-                if (FUSE) { while (!mbar_test(bar_small_empty, (tile_it & 1u) ^ 1u)) service(false); }
-                else mbar_wait(bar_small_empty, (tile_it & 1u) ^ 1u);
-                tc_fence_after();
-                ++tile_it;
+          // Split mode: ONE issue block per tap covers both of its ring uses (hi block: A_hi -> big and A_lo -> small,
+          // interleaved K step by K step; lo block: A_hi -> small) -- 12 MMAs per elect / fence / branch instead of 8 + 4.
+          // The issue loop's bookkeeping is what limits the tensor pipe here, so fewer, longer blocks win.
+          if constexpr (SPLIT) {
+            static_for<TP::NT>([&](auto T) {
+              constexpr int t = decltype(T)::value;
+              constexpr int u0 = 2 * t, u1 = 2 * t + 1;
+              constexpr bool outer = TP::outer(t);
+              constexpr int st0 = u0 % NST, st1 = u1 % NST;
+              constexpr uint32_t tap_off = ((uint32_t)TP::dy(t) * kPitch + (uint32_t)TP::dx(t) * 128u) >> 4;
+              constexpr bool chunk_start = (t % kTPC) == 0, chunk_end = (t % kTPC) == kTPC - 1;
+              if (chunk_start) {
+                buf = sbuf;
+                acquire_acc(buf, sbuf_par ^ 1u);
+                d_base = tmem_base + (uint32_t)buf * n_cols;
+                if (++sbuf == kSplitBufs) { sbuf = 0; sbuf_par ^= 1u; }
+                if (t == 0 && s == 0) {
+                  // the tile's first small MMA overwrites the small accumulator: the previous tile's must have been read
+                  if (FUSE) { while (!mbar_test(bar_small_empty, (tile_it & 1u) ^ 1u)) service(false); }
+                  else mbar_wait(bar_small_empty, (tile_it & 1u) ^ 1u);
+                  tc_fence_after();
+                  ++tile_it;
+                }
               }
-            }
+              if (FUSE) service(false);
+#ifdef CODON_TC_EXPERIMENT
+              if (prof) c_t = clock64();
+#endif
+              if (!ready) mbar_wait(bar_b_full + 8 * st0, ((u0 / NST) & 1) ? par_odd : par_even);
+              mbar_wait(bar_b_full + 8 * st1, ((u1 / NST) & 1) ? par_odd : par_even);
+#ifdef CODON_TC_EXPERIMENT
+              if (prof) { c_wait += clock64() - c_t; n_taps += 2; }
+#endif
+              if (t + 1 < TP::NT) ready = mbar_test(bar_b_full + 8 * ((u1 + 1) % NST), (((u1 + 1) / NST) & 1) ? par_odd : par_even);
+              tc_fence_after();
+              const uint64_t bd_hi = b_base + (uint64_t)(((uint32_t)st0 * kStageBytes) >> 4);
+              const uint64_t bd_lo = b_base + (uint64_t)(((uint32_t)st1 * kStageBytes) >> 4);
+              const uint32_t idesc = outer ? idesc_half : idesc_full;
+              const uint32_t d_big = d_base + (outer ? outer_col : 0u);
+              const uint32_t d_small = tmem_base + (uint32_t)kSplitBufs * n_cols + (outer ? outer_col : 0u);
+              if (elect_one()) {
+                const uint64_t a_hi = a_base + (uint64_t)tap_off, a_lo = a_base_lo + (uint64_t)tap_off;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_f16_2sm(d_big, a_hi + 2 * k, bd_hi + 2 * k, idesc, (chunk_start && k == 0) ? 0u : 1u);
+                  umma_f16_2sm(d_small, a_lo + 2 * k, bd_hi + 2 * k, idesc, (t == 0 && k == 0) ? acc0 : 1u);
+                }
+                umma_commit_2sm(bar_b_empty + 8 * st0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16_2sm(d_small, a_hi + 2 * k, bd_lo + 2 * k, idesc, 1u);
+                umma_commit_2sm(bar_b_empty + 8 * st1);
+                if (t == TP::NT - 1) {
+                  umma_commit_2sm(bar_patch_empty + 8 * ps_hi);
+                  umma_commit_2sm(bar_patch_empty + 8 * ps);
+                }
+                if (chunk_end) umma_commit_2sm(bar_acc_full + 8 * buf);
+              }
+              __syncwarp();
+            });
+          } else if constexpr (kTapGroup == 2) {
+            // two taps (two ring stages) per issue block
+            static_for<(TP::NT + 1) / 2>([&](auto I) {
+              constexpr int t0 = 2 * decltype(I)::value, t1 = t0 + 1;
+              constexpr bool has1 = t1 < TP::NT;
+              constexpr int tb = has1 ? t1 : t0;                  // (t1 clamped for the constant expressions below)
+              constexpr int st0 = t0 % NST, st1 = tb % NST;
+              if (FUSE) service(false);
+              if (!ready) mbar_wait(bar_b_full + 8 * st0, ((t0 / NST) & 1) ? par_odd : par_even);
+              if (has1) mbar_wait(bar_b_full + 8 * st1, ((tb / NST) & 1) ? par_odd : par_even);
+              if (tb + 1 < TP::NT) ready = mbar_test(bar_b_full + 8 * ((tb + 1) % NST), (((tb + 1) / NST) & 1) ? par_odd : par_even);
+              tc_fence_after();
+              if (elect_one()) {
+                auto issue_tap = [&](auto TT) {
+                  constexpr int t = decltype(TT)::value;
+                  constexpr bool outer = TP::outer(t);
+                  constexpr int st = t % NST;
+                  constexpr uint32_t tap_off = ((uint32_t)TP::dy(t) * kPitch + (uint32_t)TP::dx(t) * 128u) >> 4;
+                  const uint64_t bdesc = b_base + (uint64_t)(((uint32_t)st * kStageBytes) >> 4);
+                  const uint32_t idesc = outer ? idesc_half : idesc_full;
+                  const uint32_t d0 = d_base + (outer ? outer_col : 0u);
+#pragma unroll
+                  for (int j = 0; j < NACC; ++j) {
+                    if (j < nacc_rt) {
+                      const uint32_t sub_off = ((uint32_t)(j / G::NAX) * kTcSubH * kPitch + (uint32_t)(j % G::NAX) * kTcSubW * 128u) >> 4;
+                      const uint64_t adesc = a_base + (uint64_t)(tap_off + sub_off);
+                      const uint32_t d = d0 + (uint32_t)j * n_cols;
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) {
+                        const uint32_t acc = (t == 0 && k == 0) ? acc0 : 1u;
+                        if (OPERAND == TC_TF32) umma_tf32_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                        else                    umma_f16_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                      }
+                    }
+                  }
+                  umma_commit_2sm(bar_b_empty + 8 * st);
+                  if (t == TP::NT - 1) {
+                    umma_commit_2sm(bar_patch_empty + 8 * ps_hi);
+                    if (last_slab) umma_commit_2sm(bar_acc_full + 8 * buf);
+                  }
+                };
+                issue_tap(std::integral_constant<int, t0>{});
+                if constexpr (has1) issue_tap(std::integral_constant<int, tb>{});
+              }
+              __syncwarp();
+            });
+          } else
+          static_for<TP::NT>([&](auto T) {
+            constexpr int t = decltype(T)::value;
+            constexpr bool outer = TP::outer(t);
+            constexpr int st = t % NST;
+            constexpr uint32_t tap_off = ((uint32_t)TP::dy(t) * kPitch + (uint32_t)TP::dx(t) * 128u) >> 4;
             if (FUSE) service(false);
 #ifdef CODON_TC_EXPERIMENT
             if (prof) c_t = clock64();
 #endif
-            if (!ready) mbar_wait(bar_b_full + 8 * st, ((u / NST) & 1) ? par_odd : par_even);
+            if (!ready) mbar_wait(bar_b_full + 8 * st, ((t / NST) & 1) ? par_odd : par_even);
 #ifdef CODON_TC_EXPERIMENT
             if (prof) { c_wait += clock64() - c_t; ++n_taps; }
 #endif
-            if (u + 1 < NU) ready = mbar_test(bar_b_full + 8 * ((u + 1) % NST), (((u + 1) / NST) & 1) ? par_odd : par_even);
+            if (t + 1 < TP::NT) ready = mbar_test(bar_b_full + 8 * ((t + 1) % NST), (((t + 1) / NST) & 1) ? par_odd : par_even);
             tc_fence_after();
             const uint64_t bdesc = b_base + (uint64_t)(((uint32_t)st * kStageBytes) >> 4);
             const uint32_t idesc = outer ? idesc_half : idesc_full;
             const uint32_t d0 = d_base + (outer ? outer_col : 0u);
             if (elect_one()) {
-              // split: the hi weight block multiplies the hi and the lo activation patch, the lo block the hi patch
-              constexpr int ngroups = (SPLIT && plane == 0) ? 2 : 1;
-#if CODON_SPLIT_INTERLEAVE
-              if (SPLIT && plane == 0) {
-                const uint32_t d_small = tmem_base + (uint32_t)kSplitBufs * n_cols + (outer ? outer_col : 0u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  umma_f16_2sm(d0, a_base + (uint64_t)tap_off + 2 * k, bdesc + 2 * k, idesc, ((t % kTPC) == 0 && k == 0) ? 0u : 1u);
-                  umma_f16_2sm(d_small, a_base_lo + (uint64_t)tap_off + 2 * k, bdesc + 2 * k, idesc, (u == 0 && k == 0) ? acc0 : 1u);
-                }
-              } else
-#endif
+              for (int j = 0; j < NACC; ++j) {
+                if (j < nacc_rt && !TC2_DBG(p, 8)) {
+                  // sub-tile j = (jx, jy): + jy*16 patch rows + jx*8 pixels
+                  const uint32_t sub_off = ((uint32_t)(j / G::NAX) * kTcSubH * kPitch + (uint32_t)(j % G::NAX) * kTcSubW * 128u) >> 4;
+                  const uint64_t adesc = a_base + (uint64_t)(tap_off + sub_off);
+                  const uint32_t d = d0 + (uint32_t)j * n_cols;
 #pragma unroll
-              for (int g = 0; g < ngroups; ++g) {
-#pragma unroll
-                for (int j = 0; j < NACC; ++j) {
-                  if (j < nacc_rt && !TC2_DBG(p, 8)) {
-                    // sub-tile j = (jx, jy): + jy*16 patch rows + jx*8 pixels
-                    const uint32_t sub_off = ((uint32_t)(j / G::NAX) * kTcSubH * kPitch + (uint32_t)(j % G::NAX) * kTcSubW * 128u) >> 4;
-                    const uint64_t adesc = (g == 0 ? a_base : a_base_lo) + (uint64_t)(tap_off + sub_off);
-                    // split: hi*hi -> big accumulator, lo*hi and hi*lo -> small accumulator (n_cols further)
-                    const bool to_small = SPLIT && !(plane == 0 && g == 0);
-                    const uint32_t d = SPLIT ? (to_small ? tmem_base + (uint32_t)kSplitBufs * n_cols + (outer ? outer_col : 0u) : d0)
-                                             : d0 + (uint32_t)j * n_cols;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                      // +32 B per K step inside the 128-B swizzled row == +2 in the 16-B address field
-                      // accumulate flag: 0 for the first MMA into an accumulator (split: per chunk, big and small)
-                      // (big: per chunk; small: per tile -- acc0 is 0 during the tile's first slab)
-                      const uint32_t acc = SPLIT ? (to_small ? ((u == 0 && k == 0) ? acc0 : 1u)
-                                                             : (((t % kTPC) == 0 && k == 0) ? 0u : 1u))
-                                                 : ((u == 0 && g == 0 && k == 0) ? acc0 : 1u);
-                      if (OPERAND == TC_TF32) umma_tf32_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-                      else                    umma_f16_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-                    }
+                  for (int k = 0; k < 4; ++k) {
+                    // +32 B per K step inside the 128-B swizzled row == +2 in the 16-B address field
+                    const uint32_t acc = (t == 0 && k == 0) ? acc0 : 1u;
+                    if (OPERAND == TC_TF32) umma_tf32_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                    else                    umma_f16_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
                   }
                 }
               }
               umma_commit_2sm(bar_b_empty + 8 * st);
-              if (u == NU - 1) {
+              if (t == TP::NT - 1) {
                 umma_commit_2sm(bar_patch_empty + 8 * ps_hi);
-                if (SPLIT) umma_commit_2sm(bar_patch_empty + 8 * ps);
-                if (!SPLIT && last_slab) umma_commit_2sm(bar_acc_full + 8 * buf);
+                if (last_slab) umma_commit_2sm(bar_acc_full + 8 * buf);
               }
-              if (chunk_end) umma_commit_2sm(bar_acc_full + 8 * buf);
             }
-            (void)chunk_end;
             __syncwarp();
           });
           acc0 = 1;
