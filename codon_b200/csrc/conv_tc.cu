@@ -658,6 +658,17 @@ __device__ __forceinline__ Tile2 decode_tile2(const TcKParams& p, int item, int 
   return r;
 }
 
+// What the MMA issuer needs of a work item: its job and how many accumulators it covers (no tile coordinates: the
+// issuer's loop is the critical path of the kernel, and the full decode is half a dozen integer divisions).
+template <int NACC>
+__device__ __forceinline__ void decode_job_nacc(const TcKParams& p, int item, int& job, int& nacc) {
+  int pt = item;
+  nacc = NACC;
+  if (item >= p.main_tiles) { pt = p.main_tiles + (item - p.main_tiles) / NACC; nacc = 1; }
+  const int ppj = (p.tiles_per_job + 1) >> 1;
+  job = pt >= ppj ? 1 : 0;                           // at most two jobs per launch
+}
+
 // FUSE: the launch is a 5x5 128->128 (+ReLU) convolution followed by a 1x1 128->64 convolution (confuse /
 // confuse_c / confuse_fuse, CODON_x4.py:83-84,127).  The epilogue drains each accumulator through ReLU into a
 // 16-bit K-major SWIZZLE_128B tile Y in shared memory (fence.proxy.async), the MMA issuer multiplies it with
@@ -902,7 +913,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
       int sbuf = 0;                 // split mode: next big buffer, its use parity, tiles issued so far
       uint32_t sbuf_par = 0, tile_it = 0;
       for (int item = cluster_id; item < total_items; item += nclusters) {
-        const Tile2 tl = decode_tile2<NACC>(p, item, 0);
+        struct { int job, nacc; } tl;
+        decode_job_nacc<NACC>(p, item, tl.job, tl.nacc);
         const uint32_t outer_col = (uint32_t)p.job[tl.job].outer_col;
         int buf = it % p.nbuf;
         uint32_t d_base = 0;

@@ -2,7 +2,7 @@
 """Stress run on the GPU box: random frame shapes / batch sizes / modes through the cluster conv kernels.
 
 Every case checks: finite output, run-to-run determinism (bit-exact), batch invariance (frame 0 alone == frame 0 in the
-batch, bit-exact) and agreement with the fp32 FFMA mode (<= 1e-3 for fp16 / tf32, <= 2e-2 for bf16).  A barrier-protocol
+batch, bit-exact) and agreement with the fp32 FFMA mode (<= 1e-3 for fp16 / tf32, <= 2e-2 for bf16, <= 2e-6 for f16x3).  A barrier-protocol
 bug in the persistent kernels shows up here as a watchdog trap or a mismatch.   usage: tools/gpu_stress.py [seconds]"""
 import os
 import sys
@@ -21,19 +21,23 @@ def main():
     rng = np.random.default_rng(2024)
     dev = torch.device("cuda", 0)
     engines = {}
-    for mode in ("fp32", "fp16", "bf16", "tf32"):
+    for mode in ("fp32", "fp16", "bf16", "tf32", "f16x3"):
         e = E.Engine(4, mode, 0)
         e.load_state_dict(syn.synthetic_state_dict(4, 1))
         engines[mode] = e
-    tol = {"fp16": 1e-3, "tf32": 1e-3, "bf16": 2e-2}
+    tol = {"fp16": 1e-3, "tf32": 1e-3, "bf16": 2e-2, "f16x3": 2e-6}
     t0, n, worst = time.time(), 0, {m: 0.0 for m in tol}
     while time.time() - t0 < budget:
         B = int(rng.integers(1, 4))
-        H, W = int(rng.integers(150, 520)), int(rng.integers(150, 700))
+        # mostly mid-size frames (cluster kernels, ragged tiles, tail splitting); one case in six is tiny or very narrow
+        if n % 6 == 5:
+            H, W = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        else:
+            H, W = int(rng.integers(150, 520)), int(rng.integers(150, 700))
         x, y = syn.synthetic_frames(B, H, W, int(rng.integers(1 << 30)))
         x, y = x.to(dev), y.to(dev)
         ref = engines["fp32"].forward(x[:1].contiguous(), y[:1].contiguous()).clone()
-        for mode in ("fp16", "bf16", "tf32"):
+        for mode in tol:
             e = engines[mode]
             a = e.forward(x, y).clone()
             b = e.forward(x, y).clone()
@@ -45,7 +49,7 @@ def main():
             worst[mode] = max(worst[mode], err)
             assert err <= tol[mode], (mode, B, H, W, err)
         n += 1
-    print(f"stress: {n} random cases x 3 modes in {time.time() - t0:.0f} s, all deterministic and batch-invariant; "
+    print(f"stress: {n} random cases x {len(tol)} modes in {time.time() - t0:.0f} s, all deterministic and batch-invariant; "
           f"worst max-abs vs fp32 mode: " + ", ".join(f"{m} {v:.2e}" for m, v in worst.items()))
 
 
