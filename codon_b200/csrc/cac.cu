@@ -440,7 +440,9 @@ cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* poole
     long best = -1;
     for (int h = kATH; h >= 4; --h) {
       const long tiles = (long)tiles_x * cdiv(H, h) * B;
-      const long cost = ((tiles + 591) / 592) * h;
+      // a tile costs its rows plus a fixed part (gate prologue, partially idle lanes of a short tile) worth ~2 rows:
+      // with many waves the full 8-row tile wins (measured: B = 8 bf16 0.90 of the HBM peak with 8 rows, 0.73 with 6)
+      const long cost = ((tiles + 591) / 592) * (h + 2);
       if (best < 0 || cost < best) { best = cost; th = h; }
     }
   }
