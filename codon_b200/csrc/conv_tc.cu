@@ -51,7 +51,7 @@ constexpr int kThreads = 320;                  // warp 0 producer, 1 MMA, 2-9 ep
 // highest warp id, so the latency-critical issue loop never queues behind the epilogue's ALU work.
 constexpr int kThreads2 = 352;
 constexpr int kWarpA = 8, kWarpMma = 9, kWarpB = 10;
-constexpr int kB2MaxStages = 9;                // barrier slots reserved for the weight ring of the cluster kernel
+constexpr int kB2MaxStages = 10;               // barrier slots reserved for the weight ring of the cluster kernel
 // Perf-experiment knobs of the convolution kernels (CODON_TC_DEBUG bits, cycle accounting, CODON_TC_PDL) exist only in
 // builds with -DCODON_TC_EXPERIMENT: the MMA issue loop is latency-bound, every extra instruction in it costs
 // throughput, and a product library does not read the environment.
@@ -140,6 +140,19 @@ template <int KIND> struct Taps {
     return u;
   }
 };
+// Weight-ring depth of the cluster kernel.  The split-fp16 pair kernel streams two short blocks per tap (258-384 cycles
+// of MMA work each): five stages are ~1500 cycles of look-ahead, less than the L2 -> shared-memory latency under load
+// (its issuer spent 47 % of its time waiting for weights, profiles/r02_pair_ring.txt), and its 30 KB patches leave room
+// for ten.
+// The pair kernels of the other modes wait for weights too (95 of 490 cycles per tap at 5 stages), but ten stages there
+// measured SLOWER (bf16 0.78 -> 0.87 ms, tf32 1.54 -> 1.59 ms per step, profiles/r02_pair_ring.txt): 25 taps do not
+// divide by ten, so the tap loops exist twice (the ring pattern repeats every two slabs, kPeriod below) and the 51 KB
+// patches drop from three stages to two.  The two-phase machinery stays (any stage count whose pattern repeats within
+// two slabs keeps compile-time stage indices); only the split pair kernel uses a deeper ring.
+template <int KIND, int OPERAND> struct Ring {
+  static constexpr int NST = (KIND == TK_PAIR && OPERAND == TC_SPLIT16) ? 10 : Taps<KIND>::NST;
+};
+__host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
 template <typename F, int... Is>
 __device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, Is...>) {
   (f(std::integral_constant<int, Is>{}), ...);
@@ -686,10 +699,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   using TP = Taps<KIND>;
   // Weight ring: NST stages whose count divides the taps of a slab, so that the stage of tap t (t % NST) and the
   // use count inside a slab (t / NST) are compile-time constants; the only run-time state is one parity bit per slab.
-  constexpr int NST = TP::NST;
+  constexpr int NST = Ring<KIND, OPERAND>::NST;
   constexpr uint32_t kStageBytes = TP::kStageBytes;
-  static_assert(TP::NT % NST == 0 && NST <= kB2MaxStages, "ring must divide the tap count");
-  constexpr int kUsesPerSlab = (OPERAND == TC_SPLIT16 ? 2 : 1) * TP::NT / NST;   // odd (1, 5): a stage's parity flips per slab; even (split): it does not
+  constexpr int kUsesOfSlab = (OPERAND == TC_SPLIT16 ? 2 : 1) * TP::NT;          // ring uses per slab
+  constexpr int kPeriod = NST / cgcd(kUsesOfSlab, NST);          // slabs after which the ring pattern repeats (1 or 2)
+  constexpr int kUsesPerSlab = kPeriod * kUsesOfSlab / NST;      // uses of one stage per period; odd: its parity flips per period
+  static_assert(NST <= kB2MaxStages && kPeriod <= 2, "weight ring geometry");
   constexpr int Y16 = OPERAND == TC_BF16 ? TC_BF16 : TC_F16;   // tf32 mode stages Y in fp16 (same 10-bit mantissa)
   // Split-fp16 operands (F16X3 mode): per 64-channel slab TWO activation patches (hi, lo planes) and per tap TWO
   // weight blocks (hi, lo) -- ring "uses" u = 2 * tap + plane -- and three MMA groups per tap: A_hi*B_hi and
@@ -793,7 +808,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     }
   } else if (warp == kWarpB) {
     // ================================ B producer (both CTAs): this CTA's half of every weight block
-    uint32_t slab_par = 0;                       // parity of the ring uses of the current slab (flips per slab)
+    uint32_t slab_par = 0;                       // parity of the ring uses of the current period (flips per period)
+    int phase = 0;                               // slab inside the period (kPeriod == 2: pair kernels with ten stages)
     const uint32_t full_leader = mapa_u32(bar_b_full, 0);
     if (FUSE && elect_one()) {
       // resident 1x1 weights: this CTA's 32 of the 64 output rows, per job and 128-byte K slab
@@ -813,12 +829,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
       const CUtensorMap* bm = tl.job ? &bmap1 : &bmap0;
       for (int s = 0; s < p.nslab; ++s) {
         const int slab_row0 = (int)(((uint32_t)s * p.slab_bytes) >> 7);
+        auto produce_slab = [&](auto PH) {
+        constexpr int ph = decltype(PH)::value;
         static_for<NU>([&](auto U) {
           constexpr int u = decltype(U)::value;
           constexpr int t = SPLIT ? u / 2 : u, plane = SPLIT ? (u & 1) : 0, npl = SPLIT ? 2 : 1;
           constexpr bool outer = TP::outer(t);
-          constexpr int st = u % NST;
-          mbar_wait(bar_b_empty + 8 * st, slab_par ^ (uint32_t)((u / NST) & 1) ^ 1u);
+          constexpr int ru = ph * NU + u;          // use index inside the period
+          constexpr int st = ru % NST;
+          mbar_wait(bar_b_empty + 8 * st, slab_par ^ (uint32_t)((ru / NST) & 1) ^ 1u);
           if (elect_one()) {
             // this CTA's half of the block: rows [rank * rows/2, (rank + 1) * rows/2) in 32-row (4 KB) boxes
             const int rows = KIND == TK_PAIR ? (outer ? 64 : 128) : tap_rows;
@@ -834,7 +853,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           }
           __syncwarp();
         });
-        slab_par ^= (uint32_t)(kUsesPerSlab & 1);
+        };
+        if (kPeriod == 1 || phase == 0) produce_slab(std::integral_constant<int, 0>{});
+        else produce_slab(std::integral_constant<int, kPeriod - 1>{});
+        if (++phase == kPeriod) { phase = 0; slab_par ^= (uint32_t)(kUsesPerSlab & 1); }
       }
     }
   } else if (warp == kWarpMma) {
@@ -842,6 +864,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     if (leader) {
       int ps = 0;
       uint32_t pph = 0, slab_par = 0;
+      int phase = 0;
       int it = 0;
       const uint64_t desc_a = umma_desc_hi(kPitch), desc_b = umma_desc_hi(1024);
       const uint64_t b_base = desc_b | desc_addr(s_b);
@@ -942,7 +965,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           // Straight-line code per tap: the A start address is the patch shifted by (dy rows, dx pixels), the ring
           // stage and its barriers are immediates.  The phase test of the NEXT tap's weights is issued before this
           // tap's MMAs so that its latency hides behind their issue.
-          bool ready = mbar_test(bar_b_full, par_even);
+          static_assert(kPeriod == 1 || (!SPLIT && kTapGroup == 1), "two-phase ring: generic tap loop only");
+          bool ready = (kPeriod == 1 || phase == 0) ? mbar_test(bar_b_full, par_even)
+                                                    : mbar_test(bar_b_full + 8 * (((kPeriod - 1) * NU) % NST),
+                                                                ((((kPeriod - 1) * NU) / NST) & 1) ? par_odd : par_even);
           // Split mode: ONE issue block per tap covers both of its ring uses (hi block: A_hi -> big and A_lo -> small,
           // interleaved K step by K step; lo block: A_hi -> small) -- 12 MMAs per elect / fence / branch instead of 8 + 4.
           // The issue loop's bookkeeping is what limits the tensor pipe here, so fewer, longer blocks win.
@@ -1048,21 +1074,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
               }
               __syncwarp();
             });
-          } else
+          } else {
+          auto issue_slab = [&](auto PH) {
+          constexpr int ph = decltype(PH)::value;
           static_for<TP::NT>([&](auto T) {
             constexpr int t = decltype(T)::value;
             constexpr bool outer = TP::outer(t);
-            constexpr int st = t % NST;
+            constexpr int ru = ph * TP::NT + t;      // use index inside the ring period
+            constexpr int st = ru % NST;
             constexpr uint32_t tap_off = ((uint32_t)TP::dy(t) * kPitch + (uint32_t)TP::dx(t) * 128u) >> 4;
             if (FUSE) service(false);
 #ifdef CODON_TC_EXPERIMENT
             if (prof) c_t = clock64();
 #endif
-            if (!ready) mbar_wait(bar_b_full + 8 * st, ((t / NST) & 1) ? par_odd : par_even);
+            if (!ready) mbar_wait(bar_b_full + 8 * st, ((ru / NST) & 1) ? par_odd : par_even);
 #ifdef CODON_TC_EXPERIMENT
             if (prof) { c_wait += clock64() - c_t; ++n_taps; }
 #endif
-            if (t + 1 < TP::NT) ready = mbar_test(bar_b_full + 8 * ((t + 1) % NST), (((t + 1) / NST) & 1) ? par_odd : par_even);
+            if (t + 1 < TP::NT) ready = mbar_test(bar_b_full + 8 * ((ru + 1) % NST), (((ru + 1) / NST) & 1) ? par_odd : par_even);
             tc_fence_after();
             const uint64_t bdesc = b_base + (uint64_t)(((uint32_t)st * kStageBytes) >> 4);
             const uint32_t idesc = outer ? idesc_half : idesc_full;
@@ -1092,8 +1121,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             }
             __syncwarp();
           });
+          };
+          if (kPeriod == 1 || phase == 0) issue_slab(std::integral_constant<int, 0>{});
+          else issue_slab(std::integral_constant<int, kPeriod - 1>{});
+          }
           acc0 = 1;
-          slab_par ^= (uint32_t)(kUsesPerSlab & 1);
+          if (++phase == kPeriod) { phase = 0; slab_par ^= (uint32_t)(kUsesPerSlab & 1); }
           if (++ps == p.npb) { ps = 0; pph ^= 1; }
         }
         if (FUSE) {
@@ -1695,7 +1728,7 @@ cudaError_t launch_nacc2(const CUtensorMap& tmap, const CUtensorMap& tmapj1, con
     sms_of_dev[dev].store(num_sms, std::memory_order_release);
   }
   // fused mode adds the resident 1x1 weights (16 KB; split: 32 KB) and the Y staging tile (32 KB) behind the B ring
-  const size_t smem = setup_geometry<NACC>(kp, Taps<KIND>::NST * Taps<KIND>::kStageBytes + (FUSE ? (OPERAND == TC_SPLIT16 ? 65536 : 49152) : 0),
+  const size_t smem = setup_geometry<NACC>(kp, Ring<KIND, OPERAND>::NST * Taps<KIND>::kStageBytes + (FUSE ? (OPERAND == TC_SPLIT16 ? 65536 : 49152) : 0),
                                            OPERAND == TC_SPLIT16);
   if (!smem) return cudaErrorInvalidConfiguration;
   if (kp.ks != Taps<KIND>::KS || (uint32_t)kp.n_cols * 64u > Taps<KIND>::kStageBytes) return cudaErrorInvalidValue;
