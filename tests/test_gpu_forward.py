@@ -160,6 +160,20 @@ def test_ragged_and_tiny_shapes():
         assert float((outs - ref).abs().max()) <= 2e-6, (h, w)
 
 
+def test_narrow_frames_in_a_large_batch_use_the_cell_statistics_buffer_safely():
+    """One-pixel-wide, tall frames in a batch large enough for the fused cluster kernels: the per-cell statistics chunks
+    (one per eight 8 x 16-pixel cells) outnumber the 256-pixel chunks the partial buffer used to be sized for."""
+    sd = orc.synthetic_state_dict(4, 0)
+    x, y = orc.synthetic_frames(17, 300, 1, 31)
+    with torch.no_grad():
+        ref = orc.forward(sd, x[16:17].double(), y[16:17].double()).float()
+    for mode, tol in (("bf16", 2e-2), ("tf32", 1e-3), ("f16x3", 2e-6)):
+        net = _net(4, 0, mode)
+        with torch.no_grad():
+            out = net(x.cuda(), y.cuda())
+        assert float((out[16:17].cpu() - ref).abs().max()) <= tol, mode
+
+
 def test_cluster_kernels_ragged_frame_odd_tile_count():
     """203 x 331: large enough for the 2-CTA cluster kernels (>= 148 tiles per job), ragged in both directions
     (partial sub-tiles, TMA zero fill on every border) and with an ODD tile count per job (the peer CTA of the last

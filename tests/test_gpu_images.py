@@ -147,6 +147,36 @@ def test_driver_end_to_end_on_bundled_images(golden_dir, tmp_path, capsys):
     assert "Tsukuba.png" in log and log.strip().splitlines()[-2] == "10"
 
 
+def test_driver_with_true_low_resolution_depth(golden_dir, tmp_path):
+    """--lr-depth: the driver uploads the LR depth as uint8 (s^2 fewer bytes) and up-samples it on the GPU with
+    cv2.INTER_CUBIC semantics; the result must match running the driver on depth maps pre-upsampled by cv2 itself
+    (the reference's offline "Bicubic/X4" step, test.py:77) to within the rounding of that offline uint8 image."""
+    import cv2
+    import sys
+    img = os.path.join(golden_dir, "images")
+    names = sorted(os.listdir(os.path.join(img, "gray")))[:3]
+    lr_dir, up_dir, col_dir, lab_dir = (tmp_path / d for d in ("lr", "up", "col", "lab"))
+    for d in (lr_dir, up_dir, col_dir, lab_dir):
+        d.mkdir()
+    for n in names:
+        lab = _imread(os.path.join(img, "label", n))
+        H, W = lab.shape
+        lr = cv2.resize(lab, (W // 4, H // 4), interpolation=cv2.INTER_AREA)
+        up = np.clip(cv2.resize(lr.astype(np.float32) / 255, (W, H), interpolation=cv2.INTER_CUBIC), 0, 1)
+        cv2.imwrite(str(lr_dir / n), lr)
+        cv2.imwrite(str(up_dir / n), np.round(up * 255).astype(np.uint8))
+        cv2.imwrite(str(col_dir / n), _imread(os.path.join(img, "gray", n)))
+        cv2.imwrite(str(lab_dir / n), lab)
+    common = ["--gpus", "0", "--scale", "4", "--mode", "tf32", "--input-color", str(col_dir), "--label", str(lab_dir),
+              "--logfile", "", "--seed", "1"]
+    a = driver.main(common + ["--input-depth", str(up_dir), "--lr-depth", str(lr_dir), "--out", str(tmp_path / "o1") + "/"])
+    b = driver.main(common + ["--input-depth", str(up_dir), "--out", str(tmp_path / "o2") + "/"])
+    sys.stdout = sys.__stdout__
+    assert a[2] == b[2] == 3
+    print(f"--lr-depth: mean RMSE {a[0]:.4f} SSIM {a[1]:.5f}; pre-upsampled uint8 input: {b[0]:.4f} {b[1]:.5f}")
+    assert abs(a[0] - b[0]) < 0.1 and abs(a[1] - b[1]) < 2e-3        # the offline path rounds the input to grey levels
+
+
 def test_evaluationresults_and_ssim_exact_dropins(golden_dir):
     metrics = json.load(open(os.path.join(golden_dir, "metrics.json")))
     img = os.path.join(golden_dir, "images")
