@@ -26,7 +26,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
     assert d["vs_baseline"] is None and d["gpu_launches"] == 0
     # the reference's own classes when oracle/_ref has been built (oracle/build_ref.py), the oracle port otherwise
-    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "CODON_X4", "CODON_x4.py"))
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "CODON_X4.zip"))
     assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
     assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
