@@ -104,13 +104,6 @@ enum TcKind : int { TK_3X3 = 0, TK_5X5 = 1, TK_PAIR = 2 };
 #ifndef CODON_SPLIT_TPC_5X5
 #define CODON_SPLIT_TPC_5X5 5
 #endif
-// non-split kernels: taps issued per elect / fence / branch block (1 = one tap per block as in round 1; 2 = two taps,
-// i.e. two ring stages awaited and released per block -- the issue loop's bookkeeping limits the tensor pipe).
-// Same-session A/B on B200 (profiles/r02_ab_tap_group.txt): 5x5 128->128 fused +5.5 % (bf16: 1.62 -> 1.71 PFLOP/s),
-// +2.5 % (tf32); the 3x3 || 5x5 pair and the 3x3 layers do not move (pair tf32 -2 %), so only the 5x5 kind uses 2.
-#ifndef CODON_TC_TAP_GROUP
-#define CODON_TC_TAP_GROUP 0      // 0: per kernel kind (5x5: 2, others: 1)
-#endif
 template <int KIND> struct Taps {
   static constexpr int KS = KIND == TK_3X3 ? 3 : 5;
   static constexpr int NT = KS * KS;
@@ -140,6 +133,47 @@ template <int KIND> struct Taps {
     return u;
   }
 };
+// Column structure of the 5-wide kinds (TK_5X5, TK_PAIR).  The issue order is dx outer / dy inner, so a "column" is the
+// five taps 5c .. 5c + 4 that share dx.  Every column of a kind looks the same to the weight ring (its uses are a whole
+// number of ring revolutions) and to the split mode's accumulation chunks, so the MMA issuer and the weight producer
+// are LOOPS over columns whose bodies are straight-line per tap: only dx (one descriptor add), one ring parity bit and
+// the first / last-column flags are run-time values.  Why: the fully unrolled 25-tap loops were 43 KB (issuer) +
+// 17-32 KB (weight producer) of SASS per kernel next to ~25 KB of epilogue code, against a 32 KB instruction cache
+// (L1.5) -- the latency-critical single-warp loops ran out of L2.  Pair kernels have two column types: type 0 (columns
+// 0-2 of the centre-first order: three inner taps feeding both convolutions, then two 5x5-only border taps) and type 1
+// (columns 3-4: border taps only).
+#ifndef CODON_TC_COLROLL
+#define CODON_TC_COLROLL 1
+#endif
+// Taps (ring stages) per elect / fence / branch block of the non-split issuer inside a column.  The issue loop's
+// bookkeeping limits the tensor pipe: two taps per block measured +5.5 % (bf16) / +2.5 % (tf32) on the fused 5x5 kernels
+// (profiles/r02_ab_tap_group.txt); the 3x3 || 5x5 pair does not move (tf32 -2 %), so only the 5x5 kind groups.
+#ifndef CODON_TC_COL_GROUP
+#define CODON_TC_COL_GROUP 0      // 0: per kind -- 5x5: 2 (blocks of 2 + 2 + 1 taps per column); pair: 1
+#endif
+template <int KIND> struct Cols {
+  using TP = Taps<KIND>;
+  __host__ __device__ static constexpr int ntypes() { return KIND == TK_PAIR ? 2 : 1; }
+  __host__ __device__ static constexpr int type_of(int c) { return KIND == TK_PAIR && c >= 3 ? 1 : 0; }
+  __host__ __device__ static constexpr bool outer(int ct, int i) { return KIND == TK_PAIR && (ct == 1 || i >= 3); }
+  // pair plans: 64-row units of a column's weight stream that precede its tap i / that precede column c
+  __host__ __device__ static constexpr int units_in_col(int ct, int i) { return ct == 1 ? i : (i < 3 ? 2 * i : 6 + (i - 3)); }
+  __host__ __device__ static constexpr int units_before_col(int c) { return c < 3 ? 8 * c : 24 + 5 * (c - 3); }
+  // the column view must be the tap schedule the weights were packed with
+  __host__ __device__ static constexpr bool consistent() {
+    if (KIND == TK_3X3) return true;
+    for (int c = 0; c < 5; ++c)
+      for (int i = 0; i < 5; ++i) {
+        const int t = 5 * c + i;
+        if (TP::dx(t) != TP::ord(c) || TP::dy(t) != TP::ord(i)) return false;
+        if (TP::outer(t) != outer(type_of(c), i)) return false;
+        if (KIND == TK_PAIR && TP::units_before(t) != units_before_col(c) + units_in_col(type_of(c), i)) return false;
+      }
+    return true;
+  }
+};
+static_assert(Cols<TK_5X5>::consistent() && Cols<TK_PAIR>::consistent(), "column view of the tap schedule");
+
 // Weight-ring depth of the cluster kernel.  The split-fp16 pair kernel streams two short blocks per tap (258-384 cycles
 // of MMA work each): five stages are ~1500 cycles of look-ahead, less than the L2 -> shared-memory latency under load
 // (its issuer spent 47 % of its time waiting for weights, profiles/r02_pair_ring.txt), and its 30 KB patches leave room
@@ -722,7 +756,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   constexpr int NU = SPLIT ? 2 * TP::NT : TP::NT;                // weight-ring uses per slab
   constexpr int kTPC = KIND == TK_3X3 ? CODON_SPLIT_TPC_3X3 : CODON_SPLIT_TPC_5X5;   // taps per accumulation chunk
   constexpr int kSplitBufs = 3;
-  constexpr int kTapGroup = CODON_TC_TAP_GROUP ? CODON_TC_TAP_GROUP : (KIND == TK_5X5 ? 2 : 1);
+  // column-rolled tap loops (5x5 and pair kinds, see Cols): uses of the weight ring per column and the change of the
+  // ring's revolution parity per column
+  constexpr bool kColRoll = CODON_TC_COLROLL != 0 && KIND != TK_3X3;
+  using CL = Cols<KIND>;
+  constexpr int kNpl = SPLIT ? 2 : 1;
+  constexpr int CU = 5 * kNpl;
+  constexpr uint32_t kColFlip = (uint32_t)((CU / NST) & 1);
+  constexpr int kColGroup = CODON_TC_COL_GROUP ? CODON_TC_COL_GROUP : (KIND == TK_5X5 ? 2 : 1);   // taps per issue block
+  using G_ = Geo<NACC>;
+  static_assert(!kColRoll || (CU % NST == 0 && (kTPC == 1 || kTPC == 5)), "a column is whole ring revolutions and whole chunks");
   static_assert(TP::NT % kTPC == 0, "chunks must tile the taps of a slab");
   static_assert(!SPLIT || NACC == 1, "split mode: one accumulator (big + small, double-buffered) per tile");
   constexpr uint32_t kPitch = (uint32_t)(G::TW + TP::KS - 1) * 128u;   // patch row pitch in bytes (== p.pw * 128)
@@ -824,11 +867,49 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     __syncwarp();
     // rows (128 B) of one tap's weight block: the pair plan mixes 128-row (inner) and 64-row (outer) blocks
     const int tap_rows = p.n_cols;
+    uint32_t par = 0;                            // column-rolled loops: parity of the ring revolution at the column's start
     for (int item = cluster_id; item < total_items; item += nclusters) {
       const Tile2 tl = decode_tile2<NACC>(p, item, (int)rank);
       const CUtensorMap* bm = tl.job ? &bmap1 : &bmap0;
       for (int s = 0; s < p.nslab; ++s) {
         const int slab_row0 = (int)(((uint32_t)s * p.slab_bytes) >> 7);
+        if constexpr (kColRoll) {
+          // one column of taps: CU ring uses in issue order (split: use v = 2 * tap + plane); `first` = 128-byte rows of
+          // the slab's weight stream that precede the column, per plane
+          auto produce_column = [&](auto CT, const int first) {
+            constexpr int ct = decltype(CT)::value;
+            static_for<CU>([&](auto V) {
+              constexpr int v = decltype(V)::value, i = v / kNpl, plane = v % kNpl, st = v % NST;
+              constexpr uint32_t pf = (uint32_t)((v / NST) & 1);
+              constexpr bool outer = CL::outer(ct, i);
+              mbar_wait(bar_b_empty + 8 * st, par ^ pf ^ 1u);
+              if (elect_one()) {
+                // this CTA's half of the block: rows [rank * rows/2, (rank + 1) * rows/2) in 32-row (4 KB) boxes
+                const int rows = KIND == TK_PAIR ? (outer ? 64 : 128) : tap_rows;
+                const int row0 = slab_row0 + kNpl * (first + (KIND == TK_PAIR ? CL::units_in_col(ct, i) * 64 : i * tap_rows)) +
+                                 plane * rows + (int)rank * (rows >> 1);
+                if (TC2_DBG(p, 2)) { if (leader) mbar_arrive(bar_b_full + 8 * st); }
+                else {
+                  if (leader) mbar_expect_tx(bar_b_full + 8 * st, (uint32_t)rows << 7);
+                  const uint32_t dst = s_b + (uint32_t)st * kStageBytes;
+                  tma_load_2d_2sm(dst, bm, full_leader + 8 * st, 0, row0);
+                  if (rows > 64) tma_load_2d_2sm(dst + 4096, bm, full_leader + 8 * st, 0, row0 + 32);
+                }
+              }
+              __syncwarp();
+            });
+            par ^= kColFlip;
+          };
+          if constexpr (KIND == TK_PAIR) {
+#pragma unroll 1
+            for (int c = 0; c < 3; ++c) produce_column(std::integral_constant<int, 0>{}, CL::units_before_col(c) * 64);
+#pragma unroll 1
+            for (int c = 3; c < 5; ++c) produce_column(std::integral_constant<int, 1>{}, CL::units_before_col(c) * 64);
+          } else {
+#pragma unroll 1
+            for (int c = 0; c < 5; ++c) produce_column(std::integral_constant<int, 0>{}, 5 * c * tap_rows);
+          }
+        } else {
         auto produce_slab = [&](auto PH) {
         constexpr int ph = decltype(PH)::value;
         static_for<NU>([&](auto U) {
@@ -857,6 +938,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         if (kPeriod == 1 || phase == 0) produce_slab(std::integral_constant<int, 0>{});
         else produce_slab(std::integral_constant<int, kPeriod - 1>{});
         if (++phase == kPeriod) { phase = 0; slab_par ^= (uint32_t)(kUsesPerSlab & 1); }
+        }
       }
     }
   } else if (warp == kWarpMma) {
@@ -864,6 +946,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
     if (leader) {
       int ps = 0;
       uint32_t pph = 0, slab_par = 0;
+      uint32_t par = 0;                          // column-rolled loops: parity of the ring revolution at the column's start
       int phase = 0;
       int it = 0;
       const uint64_t desc_a = umma_desc_hi(kPitch), desc_b = umma_desc_hi(1024);
@@ -961,11 +1044,145 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
             a_base_lo = desc_a | desc_addr(s_patch + ps * p.patch_stage);
           }
           const bool last_slab = s == p.nslab - 1;
+          if constexpr (kColRoll) {
+            // Column-rolled issue loop (see Cols): a run-time loop over the five tap columns (dx), straight-line code per
+            // tap inside a column -- dy offsets, ring stages, barrier addresses and the split mode's chunk boundaries are
+            // immediates; dx is one descriptor add per column and `par` the parity of the ring revolution the column
+            // starts in.  The phase test of the NEXT block's first stage is issued before this block's MMAs.
+            bool ready = mbar_test(bar_b_full, par);
+            auto issue_column = [&](auto CT, const int dxv, const bool first_col, const bool last_col) {
+              constexpr int ct = decltype(CT)::value;
+              const uint64_t a_col = a_base + (uint64_t)((uint32_t)dxv * 8u);      // + dx pixels of 128 B, in 16-byte units
+              const uint32_t acc_first = first_col ? acc0 : 1u;                    // 0 only for the tile's very first K step
+              if constexpr (SPLIT) {
+                // ONE issue block per tap covers both of its ring uses (hi block: A_hi -> big and A_lo -> small,
+                // interleaved K step by K step; lo block: A_hi -> small): 12 MMAs per elect / fence / branch
+                const uint64_t a_col_lo = a_base_lo + (uint64_t)((uint32_t)dxv * 8u);
+                static_for<5>([&](auto I) {
+                  constexpr int i = decltype(I)::value;
+                  constexpr int v0 = 2 * i, v1 = 2 * i + 1, vn = v1 + 1;
+                  constexpr int st0 = v0 % NST, st1 = v1 % NST;
+                  constexpr uint32_t pf0 = (uint32_t)((v0 / NST) & 1), pf1 = (uint32_t)((v1 / NST) & 1);
+                  constexpr bool outer = CL::outer(ct, i);
+                  constexpr uint32_t dy_off = ((uint32_t)TP::ord(i) * kPitch) >> 4;
+                  constexpr bool chunk_start = (i % kTPC) == 0, chunk_end = (i % kTPC) == kTPC - 1;
+                  if (chunk_start) {
+                    buf = sbuf;
+                    acquire_acc(buf, sbuf_par ^ 1u);
+                    d_base = tmem_base + (uint32_t)buf * n_cols;
+                    if (++sbuf == kSplitBufs) { sbuf = 0; sbuf_par ^= 1u; }
+                    if (i == 0 && first_col && s == 0) {
+                      // the tile's first small MMA overwrites the small accumulator: the previous tile's must have been read
+                      if (FUSE) { while (!mbar_test(bar_small_empty, (tile_it & 1u) ^ 1u)) service(false); }
+                      else mbar_wait(bar_small_empty, (tile_it & 1u) ^ 1u);
+                      tc_fence_after();
+                      ++tile_it;
+                    }
+                  }
+                  if (FUSE) service(false);
+#ifdef CODON_TC_EXPERIMENT
+                  if (prof) c_t = clock64();
+#endif
+                  if (!ready) mbar_wait(bar_b_full + 8 * st0, par ^ pf0);
+                  mbar_wait(bar_b_full + 8 * st1, par ^ pf1);
+#ifdef CODON_TC_EXPERIMENT
+                  if (prof) { c_wait += clock64() - c_t; n_taps += 2; }
+#endif
+                  if constexpr (vn < CU) ready = mbar_test(bar_b_full + 8 * (vn % NST), par ^ (uint32_t)((vn / NST) & 1));
+                  else ready = mbar_test(bar_b_full, par ^ kColFlip);
+                  tc_fence_after();
+                  const uint64_t bd_hi = b_base + (uint64_t)(((uint32_t)st0 * kStageBytes) >> 4);
+                  const uint64_t bd_lo = b_base + (uint64_t)(((uint32_t)st1 * kStageBytes) >> 4);
+                  const uint32_t idesc = outer ? idesc_half : idesc_full;
+                  const uint32_t d_big = d_base + (outer ? outer_col : 0u);
+                  const uint32_t d_small = tmem_base + (uint32_t)kSplitBufs * n_cols + (outer ? outer_col : 0u);
+                  if (elect_one()) {
+                    const uint64_t a_hi = a_col + (uint64_t)dy_off, a_lo = a_col_lo + (uint64_t)dy_off;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      umma_f16_2sm(d_big, a_hi + 2 * k, bd_hi + 2 * k, idesc, (chunk_start && k == 0) ? 0u : 1u);
+                      umma_f16_2sm(d_small, a_lo + 2 * k, bd_hi + 2 * k, idesc, (i == 0 && k == 0) ? acc_first : 1u);
+                    }
+                    umma_commit_2sm(bar_b_empty + 8 * st0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16_2sm(d_small, a_hi + 2 * k, bd_lo + 2 * k, idesc, 1u);
+                    umma_commit_2sm(bar_b_empty + 8 * st1);
+                    if (i == 4 && last_col) {
+                      umma_commit_2sm(bar_patch_empty + 8 * ps_hi);
+                      umma_commit_2sm(bar_patch_empty + 8 * ps);
+                    }
+                    if (chunk_end) umma_commit_2sm(bar_acc_full + 8 * buf);
+                  }
+                  __syncwarp();
+                });
+              } else {
+                // kColGroup taps (ring stages) per issue block
+                constexpr int G = kColGroup;
+                static_for<(5 + G - 1) / G>([&](auto BK) {
+                  constexpr int i0 = decltype(BK)::value * G, cnt = (5 - i0) < G ? (5 - i0) : G, in = i0 + cnt;
+                  if (FUSE) service(false);
+#ifdef CODON_TC_EXPERIMENT
+                  if (prof) c_t = clock64();
+#endif
+                  if (!ready) mbar_wait(bar_b_full + 8 * i0, par);
+                  static_for<cnt - 1>([&](auto Q) { mbar_wait(bar_b_full + 8 * (i0 + 1 + decltype(Q)::value), par); });
+#ifdef CODON_TC_EXPERIMENT
+                  if (prof) { c_wait += clock64() - c_t; n_taps += cnt; }
+#endif
+                  if constexpr (in < 5) ready = mbar_test(bar_b_full + 8 * in, par);
+                  else ready = mbar_test(bar_b_full, par ^ kColFlip);
+                  tc_fence_after();
+                  if (elect_one()) {
+                    static_for<cnt>([&](auto Q) {
+                      constexpr int i = i0 + decltype(Q)::value;          // tap of the column == ring stage
+                      constexpr bool outer = CL::outer(ct, i);
+                      constexpr uint32_t dy_off = ((uint32_t)TP::ord(i) * kPitch) >> 4;
+                      const uint64_t bdesc = b_base + (uint64_t)(((uint32_t)i * kStageBytes) >> 4);
+                      const uint32_t idesc = outer ? idesc_half : idesc_full;
+                      const uint32_t d0 = d_base + (outer ? outer_col : 0u);
+#pragma unroll
+                      for (int j = 0; j < NACC; ++j) {
+                        if (j < nacc_rt && !TC2_DBG(p, 8)) {
+                          // sub-tile j = (jx, jy): + jy*16 patch rows + jx*8 pixels
+                          constexpr uint32_t kSubY = ((uint32_t)kTcSubH * kPitch) >> 4, kSubX = ((uint32_t)kTcSubW * 128u) >> 4;
+                          const uint64_t adesc = a_col + (uint64_t)(dy_off + (uint32_t)(j / G_::NAX) * kSubY + (uint32_t)(j % G_::NAX) * kSubX);
+                          const uint32_t d = d0 + (uint32_t)j * n_cols;
+#pragma unroll
+                          for (int k = 0; k < 4; ++k) {
+                            // +32 B per K step inside the 128-B swizzled row == +2 in the 16-B address field
+                            const uint32_t acc = (i == 0 && k == 0) ? acc_first : 1u;
+                            if (OPERAND == TC_TF32) umma_tf32_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                            else                    umma_f16_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                          }
+                        }
+                      }
+                      umma_commit_2sm(bar_b_empty + 8 * i);
+                      if (i == 4 && last_col) {
+                        umma_commit_2sm(bar_patch_empty + 8 * ps_hi);
+                        if (last_slab) umma_commit_2sm(bar_acc_full + 8 * buf);
+                      }
+                    });
+                  }
+                  __syncwarp();
+                });
+              }
+              par ^= kColFlip;
+            };
+            if constexpr (KIND == TK_PAIR) {
+#pragma unroll 1
+              for (int c = 0; c < 3; ++c) issue_column(std::integral_constant<int, 0>{}, c == 0 ? 2 : (c == 1 ? 1 : 3), c == 0, false);
+#pragma unroll 1
+              for (int c = 3; c < 5; ++c) issue_column(std::integral_constant<int, 1>{}, c == 3 ? 0 : 4, false, c == 4);
+            } else {
+#pragma unroll 1
+              for (int c = 0; c < 5; ++c) issue_column(std::integral_constant<int, 0>{}, c, c == 0, c == 4);
+            }
+          } else {
           const uint32_t par_even = slab_par, par_odd = slab_par ^ 1u;
           // Straight-line code per tap: the A start address is the patch shifted by (dy rows, dx pixels), the ring
           // stage and its barriers are immediates.  The phase test of the NEXT tap's weights is issued before this
           // tap's MMAs so that its latency hides behind their issue.
-          static_assert(kPeriod == 1 || (!SPLIT && kTapGroup == 1), "two-phase ring: generic tap loop only");
+          static_assert(kPeriod == 1 || !SPLIT, "two-phase ring: generic tap loop only");
           bool ready = (kPeriod == 1 || phase == 0) ? mbar_test(bar_b_full, par_even)
                                                     : mbar_test(bar_b_full + 8 * (((kPeriod - 1) * NU) % NST),
                                                                 ((((kPeriod - 1) * NU) / NST) & 1) ? par_odd : par_even);
@@ -1028,52 +1245,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
               }
               __syncwarp();
             });
-          } else if constexpr (kTapGroup == 2) {
-            // two taps (two ring stages) per issue block
-            static_for<(TP::NT + 1) / 2>([&](auto I) {
-              constexpr int t0 = 2 * decltype(I)::value, t1 = t0 + 1;
-              constexpr bool has1 = t1 < TP::NT;
-              constexpr int tb = has1 ? t1 : t0;                  // (t1 clamped for the constant expressions below)
-              constexpr int st0 = t0 % NST, st1 = tb % NST;
-              if (FUSE) service(false);
-              if (!ready) mbar_wait(bar_b_full + 8 * st0, ((t0 / NST) & 1) ? par_odd : par_even);
-              if (has1) mbar_wait(bar_b_full + 8 * st1, ((tb / NST) & 1) ? par_odd : par_even);
-              if (tb + 1 < TP::NT) ready = mbar_test(bar_b_full + 8 * ((tb + 1) % NST), (((tb + 1) / NST) & 1) ? par_odd : par_even);
-              tc_fence_after();
-              if (elect_one()) {
-                auto issue_tap = [&](auto TT) {
-                  constexpr int t = decltype(TT)::value;
-                  constexpr bool outer = TP::outer(t);
-                  constexpr int st = t % NST;
-                  constexpr uint32_t tap_off = ((uint32_t)TP::dy(t) * kPitch + (uint32_t)TP::dx(t) * 128u) >> 4;
-                  const uint64_t bdesc = b_base + (uint64_t)(((uint32_t)st * kStageBytes) >> 4);
-                  const uint32_t idesc = outer ? idesc_half : idesc_full;
-                  const uint32_t d0 = d_base + (outer ? outer_col : 0u);
-#pragma unroll
-                  for (int j = 0; j < NACC; ++j) {
-                    if (j < nacc_rt) {
-                      const uint32_t sub_off = ((uint32_t)(j / G::NAX) * kTcSubH * kPitch + (uint32_t)(j % G::NAX) * kTcSubW * 128u) >> 4;
-                      const uint64_t adesc = a_base + (uint64_t)(tap_off + sub_off);
-                      const uint32_t d = d0 + (uint32_t)j * n_cols;
-#pragma unroll
-                      for (int k = 0; k < 4; ++k) {
-                        const uint32_t acc = (t == 0 && k == 0) ? acc0 : 1u;
-                        if (OPERAND == TC_TF32) umma_tf32_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-                        else                    umma_f16_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-                      }
-                    }
-                  }
-                  umma_commit_2sm(bar_b_empty + 8 * st);
-                  if (t == TP::NT - 1) {
-                    umma_commit_2sm(bar_patch_empty + 8 * ps_hi);
-                    if (last_slab) umma_commit_2sm(bar_acc_full + 8 * buf);
-                  }
-                };
-                issue_tap(std::integral_constant<int, t0>{});
-                if constexpr (has1) issue_tap(std::integral_constant<int, tb>{});
-              }
-              __syncwarp();
-            });
           } else {
           auto issue_slab = [&](auto PH) {
           constexpr int ph = decltype(PH)::value;
@@ -1124,6 +1295,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
           };
           if (kPeriod == 1 || phase == 0) issue_slab(std::integral_constant<int, 0>{});
           else issue_slab(std::integral_constant<int, kPeriod - 1>{});
+          }
           }
           acc0 = 1;
           if (++phase == kPeriod) { phase = 0; slab_par ^= (uint32_t)(kUsesPerSlab & 1); }

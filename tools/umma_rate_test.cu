@@ -35,6 +35,9 @@ struct RateParams {
   int tf32;          // 1: kind::tf32 (K = 8 per instruction)
   int data;          // operand data: 0 dense random mantissas, 1 all zeros, 2 ReLU-like (half zeros, small bf16 values)
   int interleave;    // 1: K-step outer, accumulator inner (consecutive MMAs hit different accumulators)
+  int ovh;           // issue-loop overhead elements added per block (what the conv kernels' issuer does between MMA groups):
+                     // 1 mbarrier.test_wait, 2 mbarrier.try_wait, 4 tcgen05.fence::after_thread_sync, 8 a second commit,
+                     // 16 a second try_wait, 32 a polling-style branch around the try_wait (call-free slow path)
 };
 
 template <int CG, int NACC, int ORDER>
@@ -43,7 +46,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(RateParams p, unsigned lon
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
   uint8_t* sm = raw + (base - smem_u32(raw));
   const uint32_t s_a = base, s_b = base + 64 * 1024;       // A: 64 KB patch area, B: 128 KB ring
-  __shared__ uint64_t bar_done, bar_dummy;
+  __shared__ uint64_t bar_done, bar_dummy, bar_ready;
   __shared__ uint32_t tslot;
   uint32_t rank = 0;
   if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -62,6 +65,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(RateParams p, unsigned lon
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar_done)) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar_dummy)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar_ready)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_ready)) : "memory");   // phase 0 complete for good
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) {
@@ -96,6 +101,14 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(RateParams p, unsigned lon
       const int dx = p.shift ? tap % 5 : 0, dy = p.shift ? tap / 5 : 0;
       const uint64_t ad0 = hi_a | (uint64_t)(((s_a + (uint32_t)dy * pitch + (uint32_t)dx * 128u) & 0x3FFFFu) >> 4);
       const uint64_t bd = hi_b | (uint64_t)(((s_b + (uint32_t)st * b_stage) & 0x3FFFFu) >> 4);
+      if (p.ovh) {
+        const uint32_t rb = smem_u32(&bar_ready);
+        uint32_t ok = 1;
+        if (p.ovh & 1) asm volatile("{\n\t.reg .pred q;\n\tmbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok) : "r"(rb), "r"(0) : "memory");
+        if (p.ovh & 2) { if (!(p.ovh & 32) || !ok) mbar_wait(rb, 0); }
+        if (p.ovh & 16) mbar_wait(rb, 0);
+        if (p.ovh & 4) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       if (elect_one()) {
 #pragma unroll
         for (int q = 0; q < 4 * NACC; ++q) {
@@ -115,6 +128,11 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(RateParams p, unsigned lon
             else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                               ::"r"(smem_u32(&bar_dummy)), "h"((uint16_t)3) : "memory");
           }
+        }
+        if (p.ovh & 8) {
+          if (CG == 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_dummy)) : "memory");
+          else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                            ::"r"(smem_u32(&bar_dummy)), "h"((uint16_t)3) : "memory");
         }
         if (p.commit_each) {
           if (CG == 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_dummy)) : "memory");
@@ -233,6 +251,28 @@ int main(int argc, char** argv) {
       p.n = 64; p.b_rows = 32; p.shift = 1;
       snprintf(label, sizeof label, "bf16 cg2 M256 N64  nacc1 sbo %d shift", sbo);
       rc |= run<2, 1, 0>(label, p, sms & ~1, d_out);
+    }
+    return rc;
+  }
+  if (argc > 2 && atoi(argv[2]) == 4) {
+    // issue-loop overhead elements: cycles per BLOCK (4 MMAs of N = 128 = 256 cycles of tensor work, or no MMA at all)
+    for (int with_mma = 1; with_mma >= 0; --with_mma)
+      for (int ovh : {0, 1, 2, 4, 8, 16, 1 | 2 | 32, 2 | 4, 2 | 16, 2 | 4 | 8 | 16, 1 | 2 | 32 | 4 | 8 | 16}) {
+        char label[160];
+        RateParams p = {};
+        p.n = 128; p.m = 256; p.b_rows = 64; p.sbo = 2560; p.shift = 1; p.commit_each = 1; p.data = 2; p.nacc = 1; p.iters = iters * 2;
+        p.ovh = ovh;
+        snprintf(label, sizeof label, "cg2 N128 4 MMAs/block %s ovh %2d (x4 = cyc/block)", with_mma ? "MMA " : "none", ovh);
+        rc |= with_mma ? run<2, 1, 0>(label, p, sms & ~1, d_out) : run<2, 1, 3>(label, p, sms & ~1, d_out);
+      }
+    // the same with N = 64 blocks of 8 MMAs (pair kernel border taps: 344 cycles of tensor work per block)
+    for (int ovh : {0, 2, 2 | 4, 2 | 4 | 8 | 16, 1 | 2 | 32 | 4 | 8 | 16}) {
+      char label[160];
+      RateParams p = {};
+      p.n = 64; p.m = 256; p.b_rows = 32; p.sbo = 2560; p.shift = 1; p.commit_each = 1; p.data = 2; p.nacc = 2; p.iters = iters;
+      p.ovh = ovh;
+      snprintf(label, sizeof label, "cg2 N64 8 MMAs/block MMA ovh %2d (x8 = cyc/block)", ovh);
+      rc |= run<2, 2, 0>(label, p, sms & ~1, d_out);
     }
     return rc;
   }
