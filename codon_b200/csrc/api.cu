@@ -62,6 +62,7 @@ struct TcLayer {
 struct Buffers {
   // byte offsets into the workspace
   size_t xf = 0, yf = 0, of32 = 0, E = 0, F = 0, MS = 0, R2 = 0, FUSE = 0, OF = 0, pooled = 0, part = 0, sc = 0;
+  size_t gate = 0;                    // spatial gate map s_s [B,H,W] fp32 (written next to the CAC MLP, read by cac_apply)
   size_t cstat = 0, cstat_half = 0;   // per-cell channel partials of the two branches (fused conv epilogue), bytes of one
   int cells = 0;                      // 8 x 16-pixel cells per frame
   size_t total = 0;
@@ -221,6 +222,7 @@ Buffers plan_buffers(const codon_ctx* ctx, int B, int H, int W, int part_chunks 
   if (cac_cell_chunks(b.cells) > max_chunks) max_chunks = cac_cell_chunks(b.cells);
   b.part = take((size_t)B * max_chunks * 256 * 4);
   b.sc = take((size_t)B * 64 * 4);
+  b.gate = take(P * 4);             // spatial gate map s_s
   b.cstat_half = align_up((size_t)B * b.cells * 256 * sizeof(float2), 1024);
   b.cstat = take(2 * b.cstat_half);
   b.total = off + 1024;   // slack for aligning the caller's pointer
@@ -563,6 +565,8 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
     float* pooled = reinterpret_cast<float*>(ws + bf.pooled);
     float* part = reinterpret_cast<float*>(ws + bf.part);
     float* sc = reinterpret_cast<float*>(ws + bf.sc);
+    float* gate = reinterpret_cast<float*>(ws + bf.gate);
+    const CacGate cg = {pooled, ctx->cac_ws[s], gate, H, W, pool_parts, bf.px};
     // algorithmic HBM bytes: stats reads F (128e B/px); apply reads F and E, writes F (384e B/px)
     if (!hook) {
       int chunks = bf.chunks;
@@ -570,11 +574,13 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
         // fused conv path: fold the epilogue's per-cell partials (32 B per pixel) instead of re-reading F
         chunks = cac_cell_chunks(bf.cells);
         ProfScope ps(ctx, PC_CAC_STATS, P * 32, st);
-        CU_TRY(ctx, launch_cac_cell_reduce(ws + bf.cstat, ws + bf.cstat + bf.cstat_half, B, bf.cells, part, chunks, st));
+        CU_TRY(ctx, launch_cac_cell_reduce(ws + bf.cstat, ws + bf.cstat + bf.cstat_half, B, bf.cells, part, chunks, st, &cg));
       } else {
         ProfScope ps(ctx, PC_CAC_STATS, P * 128 * r.e, st);
         if (tc_mode) CU_TRY(ctx, launch_cac_chan_stats(ws + bf.F, ctx->act, B, H, W, part, bf.chunks, st));
         else CU_TRY(ctx, launch_cac_stats(ws + bf.F, ctx->act, B, H, W, pooled, part, bf.chunks, st));
+        CU_TRY(ctx, launch_cac_gate(cg, B, st));
+        ctx->launches++;
       }
       ProfScope ps(ctx, PC_CAC_MLP, 0.0, st);
       CU_TRY(ctx, launch_cac_mlp(part, chunks, B, H * W, ctx->cac_w1[s], ctx->cac_b1[s], ctx->cac_w2[s],
@@ -607,12 +613,15 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
         if ((rc = halo({bf.pooled}, 8, true))) return rc;
         if ((rc = hook->gather_parts(bf.part))) return rc;
       }
+      // the gate map needs the neighbours' ChannelPool halo rows: after the exchange
+      CU_TRY(ctx, launch_cac_gate(cg, 1, st));
+      ctx->launches++;
       CU_TRY(ctx, launch_cac_mlp(part, hook->chunks_total, 1, (int)hook->global_hw, ctx->cac_w1[s], ctx->cac_b1[s],
                                  ctx->cac_w2[s], ctx->cac_b2[s], sc, st));
     }
     {
       ProfScope ps(ctx, PC_CAC_APPLY, P * 384 * r.e, st);
-      CU_TRY(ctx, launch_cac_apply(ws + bf.F, ws + bf.E, ctx->act, pooled, sc, ctx->cac_ws[s], B, H, W, st, ctx->mode == CODON_MODE_TF32, pool_parts, bf.px));
+      CU_TRY(ctx, launch_cac_apply(ws + bf.F, ws + bf.E, ctx->act, gate, sc, B, H, W, st, ctx->mode == CODON_MODE_TF32));
     }
     ctx->launches += 3;
     if ((rc = halo({bf.F}, 128))) return rc;

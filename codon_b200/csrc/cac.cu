@@ -13,6 +13,8 @@
 //
 // Algorithmic HBM bytes per pixel per stage (e = bytes per element): stats 128e, apply
 // 128e (F) + 128e (E) + 128e (store) = 512e in total.
+#include <atomic>
+#include <type_traits>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -198,6 +200,76 @@ __global__ void __launch_bounds__(256, 4) cac_chan_stats_kernel(const T* __restr
   }
 }
 
+// Spatial gate map s_s = sigmoid(conv5x5(ChannelPool)) (CAC_module.py:90-94), one 32 x 8-pixel tile per 128-thread
+// block: pooled halo (zero padding at the image border) in shared memory, two pixels per thread.  The gate used to be
+// the prologue of every cac_apply tile; computed by extra blocks of the statistics-fold launch (or by its own small
+// launch on the paths without that fold) it leaves cac_apply a pure streaming kernel with no per-tile fixed cost and no
+// wave quantisation.  Arithmetic and summation order are those of the r01 apply prologue (bit-identical gates).
+constexpr int kGTW = 32, kGTH = 8;
+__device__ __forceinline__ void gate_tile(const CacGate& g, int b, int tile) {
+  __shared__ float2 sp[kGTH + 4][kGTW + 4];
+  __shared__ float sw[50];
+  const int t = threadIdx.x;
+  const int tiles_x = (g.W + kGTW - 1) / kGTW;
+  const int ty0 = (tile / tiles_x) * kGTH, tx0 = (tile % tiles_x) * kGTW;
+  const int H = g.H, W = g.W;
+  const size_t fb = (size_t)b * H * W;
+  if (t < 50) sw[t] = g.ws[t];
+  // Every load of the block is issued before the first one is used (a loop over halo pixels and a run-time part count
+  // issues one dependent load after the other: a dozen memory latencies per block instead of one).
+  auto stage = [&](auto PARTS) {
+    constexpr int parts = decltype(PARTS)::value;
+    constexpr int kHalo = (kGTH + 4) * (kGTW + 4), kIt = (kHalo + 127) / 128;
+    float2 w[kIt][parts];
+    bool in[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int i = t + it * 128;
+      const int gy = ty0 + i / (kGTW + 4) - 2, gx = tx0 + i % (kGTW + 4) - 2;
+      in[it] = i < kHalo && gy >= 0 && gy < H && gx >= 0 && gx < W;
+#pragma unroll
+      for (int k = 0; k < parts; ++k)
+        w[it][k] = in[it] ? __ldg(reinterpret_cast<const float2*>(g.pooled + ((size_t)k * g.part_stride + fb + (size_t)gy * W + gx) * 2))
+                          : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int i = t + it * 128;
+      float2 v = w[it][0];
+      if (parts > 1) {
+        // (max, sum) partials from the 1x1 conv epilogues (2: one per branch; 4: per branch and 32-channel half)
+        // -> (max, mean) over the 128 channels
+#pragma unroll
+        for (int k = 1; k < parts; ++k) v = make_float2(fmaxf(v.x, w[it][k].x), v.y + w[it][k].y);
+        v.y *= (1.0f / 128.0f);
+      }
+      if (!in[it]) v = make_float2(0.f, 0.f);
+      if (i < kHalo) sp[i / (kGTW + 4)][i % (kGTW + 4)] = v;
+    }
+  };
+  if (g.pool_parts == 4) stage(std::integral_constant<int, 4>{});
+  else if (g.pool_parts == 2) stage(std::integral_constant<int, 2>{});
+  else stage(std::integral_constant<int, 1>{});
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < kGTH / 4; ++h) {            // rows r, r + 4
+    const int r = t / kGTW + h * 4, c = t % kGTW;
+    if (ty0 + r < H && tx0 + c < W) {
+      float acc = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+          const float2 pv = sp[r + dy][c + dx];
+          acc = fmaf(sw[dy * 5 + dx], pv.x, acc);
+          acc = fmaf(sw[25 + dy * 5 + dx], pv.y, acc);
+        }
+      g.gate[fb + (size_t)(ty0 + r) * W + tx0 + c] = sigmoidf_exact(acc);
+    }
+  }
+}
+__global__ void __launch_bounds__(128) cac_gate_kernel(const CacGate g) { gate_tile(g, blockIdx.y, blockIdx.x); }
+
 // Tensor-core modes with the fused 5x5 + 1x1 kernel: the conv epilogue already left per-channel (sum, max) partials
 // per 8 x 16-pixel cell and TMEM lane quarter (TcJob::cstat: [frame][cell][4][64] float2 per branch).  This kernel
 // folds kCellsPerChunk consecutive cells (row-major cell order of the frame) into one chunk of the `part` layout the
@@ -206,18 +278,27 @@ __global__ void __launch_bounds__(256, 4) cac_chan_stats_kernel(const T* __restr
 constexpr int kCellsPerChunk = 8;
 __global__ void __launch_bounds__(128) cac_cell_reduce_kernel(const float2* __restrict__ cstat_d,
                                                               const float2* __restrict__ cstat_c, int cells,
-                                                              int chunks, float* __restrict__ part) {
+                                                              int chunks, float* __restrict__ part, const CacGate g) {
+  if ((int)blockIdx.x >= chunks) {               // blocks [chunks, chunks + gate tiles): the spatial gate map
+    gate_tile(g, blockIdx.y, (int)blockIdx.x - chunks);
+    return;
+  }
   const int b = blockIdx.y, chunk = blockIdx.x, ch = threadIdx.x;
   const float2* src = (ch < 64 ? cstat_d : cstat_c) + (size_t)b * cells * 256 + (ch & 63);
   const int c0 = chunk * kCellsPerChunk, c1 = min(c0 + kCellsPerChunk, cells);
   float s = 0.f, m = -INFINITY;
-  for (int c = c0; c < c1; ++c) {
-    float2 v[4];
+  // all loads of the chunk first (8 cells x 4 lane quarters), then the fixed-order fold
+  float2 v[kCellsPerChunk][4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = __ldg(src + ((size_t)c * 4 + q) * 64);
+  for (int k = 0; k < kCellsPerChunk; ++k)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { s += v[q].x; m = fmaxf(m, v[q].y); }
-  }
+    for (int q = 0; q < 4; ++q)
+      v[k][q] = c0 + k < c1 ? __ldg(src + ((size_t)(c0 + k) * 4 + q) * 64) : make_float2(0.f, -INFINITY);
+#pragma unroll
+  for (int k = 0; k < kCellsPerChunk; ++k)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (c0 + k < c1) { s += v[k][q].x; m = fmaxf(m, v[k][q].y); }
   float* dst = part + ((size_t)(b * chunks + chunk) * 2) * 128;
   dst[ch] = s;
   dst[128 + ch] = m;
@@ -292,99 +373,84 @@ __global__ void __launch_bounds__(1024) cac_mlp_kernel(const float* __restrict__
   }
 }
 
-// apply tile: up to 8 x 32 pixels.  The tile HEIGHT is chosen per launch (4 .. 8 rows) so that the tile count comes close
-// to a whole number of waves of resident CTAs: at 640x480 x 1 frame, 8-row tiles are 1200 CTAs = 2.03 waves of 592 (the
-// kernel ran three waves' worth of time for two waves of work: 0.70 of the HBM peak), 6-row tiles are 1600 = 2.7 waves.
-constexpr int kATH = 8, kATW = 32;
-
+// F = F * s_c * s_s + E in place (CODON_x4.py:86-118): a pure streaming kernel over the 16-byte vectors of F / E.  The
+// gate map s_s comes from gate_tile (above), s_c from cac_mlp_kernel.  Persistent CTAs (4 per SM) walk the vectors in
+// units of 256 (one per thread) with a grid stride -- no tiles, no prologue, no partial last wave (r01 .. r02a: 8 x
+// 32-pixel tiles with the gate convolution as their prologue; one 640x480 frame was 2.03 or 2.7 waves of 592 resident
+// CTAs and ran at 0.68-0.70 of the HBM peak in bf16; this kernel: 0.80 bf16, 0.95 with fp32 storage, same-session A/B
+// profiles/r02_ab_cac_stream.txt).  The loads of the next batch are issued before the current batch is computed and
+// stored.  The walk starts at the END of F: the convolution that produced F wrote its tiles top to bottom, so the
+// bottom rows are the part of F most likely still in L2 (2-4 % over the forward walk on one frame; no effect at 8).
+#ifndef CODON_APPLY_KU
+#define CODON_APPLY_KU 2          // 16-byte vectors per thread and batch (two batches in flight)
+#endif
+#ifndef CODON_APPLY_ORDER
+#define CODON_APPLY_ORDER 2       // 0: one contiguous range per CTA; 1 / 2: grid-stride units, forward / from the end
+#endif
+#ifndef CODON_APPLY_CTAS
+#define CODON_APPLY_CTAS 4        // resident CTAs per SM
+#endif
 template <typename T>
-__global__ void __launch_bounds__(256, 4) cac_apply_kernel(T* __restrict__ F, const T* __restrict__ E,
-                                                           const float* __restrict__ pooled,
-                                                           const float* __restrict__ sc,
-                                                           const float* __restrict__ ws, int H, int W,
-                                                        int tiles_x, int rnd_tf32, int pool_parts, size_t part_stride, int th) {
-  constexpr int V = Act<T>::kVec, LPP = 128 / V, PH = kATH + 4, PW = kATW + 4;
-  __shared__ float2 sp[PH][PW];
-  __shared__ float sw[50], ssc[64], sss[kATH * kATW];
-  const int b = blockIdx.y, t = threadIdx.x;
-  const int ty0 = (blockIdx.x / tiles_x) * th, tx0 = (blockIdx.x % tiles_x) * kATW;   // th <= kATH rows per tile
-  const size_t fb = (size_t)b * H * W;
-  // The tile's F / E vectors do not depend on the gate: the first batch of kU + kU 16-byte loads is issued before
-  // the pooled-halo staging and the 5x5 gate convolution, so HBM is busy while the CTA computes s_s (r01h: every
-  // CTA of a wave sat in that prologue at the same time with no load in flight).  Thread t owns vector
-  // i = t + k * 256 (pixel i / LPP, 16-byte group i % LPP) for k < LPP, fetched in batches of kU.
-  constexpr int kU = sizeof(typename Act<T>::Raw) > 16 ? 2 : 4, NB = LPP / kU;
-  typename Act<T>::Raw rf[kU], re[kU];
-  int pix[kU];                                   // pixel index inside the frame, -1 = outside the image
-  auto fetch = [&](int bt) {
+__global__ void __launch_bounds__(256, CODON_APPLY_CTAS) cac_apply_kernel(T* __restrict__ F, const T* __restrict__ E,
+                                                           const float* __restrict__ gate,
+                                                           const float* __restrict__ sc, size_t nvec, int HW,
+                                                           int rnd_tf32) {
+  constexpr int V = Act<T>::kVec, LPP = 128 / V;          // vectors per pixel
+  constexpr int kU = sizeof(typename Act<T>::Raw) > 16 ? CODON_APPLY_KU / 2 : CODON_APPLY_KU;   // vectors per thread and batch; two batches in flight
+  // this CTA's units of 256 vectors (one per thread): unit_of(i), i < n
+  const size_t units = (nvec + 255) / 256;
+#if CODON_APPLY_ORDER == 0
+  const size_t u0 = units * blockIdx.x / gridDim.x;
+  const size_t n = units * (blockIdx.x + 1) / gridDim.x - u0;
+  auto unit_of = [&](size_t i) { return u0 + i; };
+#else
+  const size_t n = (units + gridDim.x - 1 - blockIdx.x) / gridDim.x;
+  auto unit_of = [&](size_t i) {
+    const size_t u = blockIdx.x + i * gridDim.x;
+    return CODON_APPLY_ORDER == 2 ? units - 1 - u : u;
+  };
+#endif
+  const int t = threadIdx.x;
+  typename Act<T>::Raw af[kU], ae[kU], bf[kU], be[kU];
+  auto fetch = [&](size_t i, typename Act<T>::Raw (&f)[kU], typename Act<T>::Raw (&e)[kU]) {
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int i = t + (bt * kU + u) * 256, g = i % LPP, px = i / LPP;
-      const int gy = ty0 + px / kATW, gx = tx0 + px % kATW;
-      pix[u] = (px < th * kATW && gy < H && gx < W) ? gy * W + gx : -1;
-      if (pix[u] >= 0) {
-        const size_t o = (fb + (size_t)pix[u]) * 128 + g * V;
-        rf[u] = Act<T>::ld(F + o);
-        re[u] = Act<T>::ldg(E + o);
+    for (int k = 0; k < kU; ++k) {
+      const size_t v = unit_of(i + k) * 256 + t;
+      if (i + k < n && v < nvec) {
+        f[k] = Act<T>::ld(F + v * V);
+        e[k] = Act<T>::ldg(E + v * V);
       }
     }
   };
-  fetch(0);
-  if (t < 50) sw[t] = ws[t];
-  if (t >= 64 && t < 128) ssc[t - 64] = sc[b * 64 + t - 64];
-  for (int i = t; i < (th + 4) * PW; i += 256) {
-    const int gy = ty0 + i / PW - 2, gx = tx0 + i % PW - 2;
-    float2 v = make_float2(0.f, 0.f);
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      v = __ldg(reinterpret_cast<const float2*>(pooled + (fb + (size_t)gy * W + gx) * 2));
-      if (pool_parts > 1) {
-        // (max, sum) partials from the 1x1 conv epilogues (2: one per branch; 4: per branch and 32-channel half)
-        // -> (max, mean) over the 128 channels
-        for (int k = 1; k < pool_parts; ++k) {
-          const float2 w = __ldg(reinterpret_cast<const float2*>(pooled + ((size_t)k * part_stride + fb + (size_t)gy * W + gx) * 2));
-          v = make_float2(fmaxf(v.x, w.x), v.y + w.y);
-        }
-        v.y *= (1.0f / 128.0f);
-      }
-    }
-    sp[i / PW][i % PW] = v;
-  }
-  __syncthreads();
-  if (t < th * kATW) {
-    const int r = t / kATW, c = t % kATW;
-    float q = 0.f;
+  auto finish = [&](size_t i, const typename Act<T>::Raw (&rf)[kU], const typename Act<T>::Raw (&re)[kU]) {
 #pragma unroll
-    for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 5; ++dx) {
-        const float2 pv = sp[r + dy][c + dx];
-        q = fmaf(sw[dy * 5 + dx], pv.x, q);
-        q = fmaf(sw[25 + dy * 5 + dx], pv.y, q);
-      }
-    sss[t] = sigmoidf_exact(q);
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int bt = 0; bt < NB; ++bt) {
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int i = t + (bt * kU + u) * 256, px = i / LPP;
-      if (pix[u] >= 0) {
+    for (int k = 0; k < kU; ++k) {
+      const size_t v = unit_of(i + k) * 256 + t;
+      if (i + k < n && v < nvec) {
+        const size_t pix = v / LPP;
+        const int c0 = ((int)(v % LPP) * V) & 63;
+        const float s = __ldg(gate + pix);
+        const float* ssc = sc + (pix / (size_t)HW) * 64 + c0;
         float f[V], e[V];
-        Act<T>::unpack(rf[u], f);
-        Act<T>::unpack(re[u], e);
-        const float s = sss[px];
-        const int c0 = ((i % LPP) * V) & 63;
+        Act<T>::unpack(rf[k], f);
+        Act<T>::unpack(re[k], e);
 #pragma unroll
-        for (int j = 0; j < V; ++j) f[j] = fmaf(f[j], ssc[c0 + j] * s, e[j]);
+        for (int j = 0; j < V; ++j) f[j] = fmaf(f[j], __ldg(ssc + j) * s, e[j]);
         if (rnd_tf32) {
 #pragma unroll
           for (int j = 0; j < V; ++j) f[j] = round_tf32(f[j]);
         }
-        Act<T>::store(F + (fb + (size_t)pix[u]) * 128 + (i % LPP) * V, f);
+        Act<T>::store(F + v * V, f);
       }
     }
-    if (bt + 1 < NB) fetch(bt + 1);
+  };
+  if (n > 0) fetch(0, af, ae);
+#pragma unroll 1
+  for (size_t i = 0; i < n; i += 2 * kU) {
+    if (i + kU < n) fetch(i + kU, bf, be);
+    finish(i, af, ae);
+    if (i + 2 * kU < n) fetch(i + 2 * kU, af, ae);
+    if (i + kU < n) finish(i + kU, bf, be);
   }
 }
 
@@ -416,10 +482,21 @@ cudaError_t launch_cac_chan_stats(const void* F, int act, int B, int H, int W, f
 
 int cac_cell_chunks(int cells) { return cdiv(cells, kCellsPerChunk); }
 
+static int gate_tiles(const CacGate& g) { return cdiv(g.W, kGTW) * cdiv(g.H, kGTH); }
+
 cudaError_t launch_cac_cell_reduce(const void* cstat_d, const void* cstat_c, int B, int cells, float* part, int chunks,
-                                   cudaStream_t st) {
-  cac_cell_reduce_kernel<<<dim3(chunks, B), 128, 0, st>>>(static_cast<const float2*>(cstat_d), static_cast<const float2*>(cstat_c),
-                                                            cells, chunks, part);
+                                   cudaStream_t st, const CacGate* gate) {
+  CacGate g = {};
+  if (gate) { g = *gate; if (g.part_stride == 0) g.part_stride = (size_t)B * g.H * g.W; }
+  cac_cell_reduce_kernel<<<dim3(chunks + (gate ? gate_tiles(g) : 0), B), 128, 0, st>>>(
+      static_cast<const float2*>(cstat_d), static_cast<const float2*>(cstat_c), cells, chunks, part, g);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cac_gate(const CacGate& gate, int B, cudaStream_t st) {
+  CacGate g = gate;
+  if (g.part_stride == 0) g.part_stride = (size_t)B * g.H * g.W;
+  cac_gate_kernel<<<dim3(gate_tiles(g), B), 128, 0, st>>>(g);
   return cudaGetLastError();
 }
 
@@ -429,28 +506,31 @@ cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const f
   return cudaGetLastError();
 }
 
-cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* pooled, const float* sc,
-                             const float* ws, int B, int H, int W, cudaStream_t st, int rnd_tf32, int pool_parts,
-                             size_t part_stride) {
-  const int tiles_x = cdiv(W, kATW);
-  if (part_stride == 0) part_stride = (size_t)B * H * W;
-  // tile height: the one that needs the least (waves of 148 x 4 resident CTAs) x (rows per tile)
-  int th = kATH;
-  {
-    long best = -1;
-    for (int h = kATH; h >= 4; --h) {
-      const long tiles = (long)tiles_x * cdiv(H, h) * B;
-      // a tile costs its rows plus a fixed part (gate prologue, partially idle lanes of a short tile) worth ~2 rows:
-      // with many waves the full 8-row tile wins (measured: B = 8 bf16 0.90 of the HBM peak with 8 rows, 0.73 with 6)
-      const long cost = ((tiles + 591) / 592) * (h + 2);
-      if (best < 0 || cost < best) { best = cost; th = h; }
-    }
+cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* gate, const float* sc, int B, int H, int W,
+                             cudaStream_t st, int rnd_tf32) {
+  static std::atomic<int> sms_of_dev[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  int num_sms = sms_of_dev[dev].load(std::memory_order_acquire);
+  if (num_sms == 0) {
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    sms_of_dev[dev].store(num_sms, std::memory_order_release);
   }
-  dim3 grid(tiles_x * cdiv(H, th), B);
-  if (act == ACT_F32) cac_apply_kernel<float><<<grid, 256, 0, st>>>((float*)F, (const float*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride, th);
-  else if (act == ACT_BF16) cac_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)F, (const __nv_bfloat16*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride, th);
-  else if (act == ACT_SPLIT16) cac_apply_kernel<split16><<<grid, 256, 0, st>>>((split16*)F, (const split16*)E, pooled, sc, ws, H, W, tiles_x, 0, pool_parts, part_stride, th);
-  else cac_apply_kernel<__half><<<grid, 256, 0, st>>>((__half*)F, (const __half*)E, pooled, sc, ws, H, W, tiles_x, rnd_tf32, pool_parts, part_stride, th);
+  const int HW = H * W;
+  const size_t P = (size_t)B * HW;
+  auto go = [&](auto* f, const auto* e) {
+    using T = std::remove_pointer_t<decltype(f)>;
+    const size_t nvec = P * (128 / Act<T>::kVec);
+    const size_t units = (nvec + 255) / 256;
+    size_t grid = (size_t)num_sms * CODON_APPLY_CTAS;
+    if (grid > units) grid = units;
+    cac_apply_kernel<T><<<(unsigned)grid, 256, 0, st>>>(f, e, gate, sc, nvec, HW, rnd_tf32);
+  };
+  if (act == ACT_F32) go((float*)F, (const float*)E);
+  else if (act == ACT_BF16) go((__nv_bfloat16*)F, (const __nv_bfloat16*)E);
+  else if (act == ACT_SPLIT16) { rnd_tf32 = 0; go((split16*)F, (const split16*)E); }
+  else go((__half*)F, (const __half*)E);
   return cudaGetLastError();
 }
 

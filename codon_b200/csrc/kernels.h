@@ -42,22 +42,31 @@ cudaError_t launch_cac_stats(const void* F, int act, int B, int H, int W, float*
 // come from the 1x1 conv epilogues (two [B,H,W] float2 arrays, one per branch: (max, sum) over 64 channels).
 cudaError_t launch_cac_chan_stats(const void* F, int act, int B, int H, int W, float* part, int chunks,
                                   cudaStream_t st);
+// Spatial gate map gate[B][H][W] = sigmoid(conv5x5(ChannelPool)) (CAC_module.py:90-94).  pool_parts 1: pooled = final
+// (max, mean) [B,H,W,2]; 2 / 4: (max, sum) partial maps `part_stride` pixels apart (0: B*H*W).  ws fp32 [2][25]: max map
+// taps, then mean map taps.
+struct CacGate {
+  const float* pooled;
+  const float* ws;
+  float* gate;
+  int H, W, pool_parts;
+  size_t part_stride;
+};
+cudaError_t launch_cac_gate(const CacGate& gate, int B, cudaStream_t st);
 // fused conv path: folds the per-cell channel partials the conv epilogue wrote (conv_tc.h, TcJob::cstat; `cells` cells
-// of 8 x 16 pixels per frame and branch) into chunks of the `part` layout; chunks = cac_cell_chunks(cells).
+// of 8 x 16 pixels per frame and branch) into chunks of the `part` layout; chunks = cac_cell_chunks(cells).  With `gate`
+// the same launch also computes the spatial gate map (extra blocks).
 int cac_cell_chunks(int cells);
 cudaError_t launch_cac_cell_reduce(const void* cstat_d, const void* cstat_c, int B, int cells, float* part, int chunks,
-                                   cudaStream_t st);
+                                   cudaStream_t st, const CacGate* gate = nullptr);
 // mlp: deterministic reduce of the partials, MLP 128->8->64 on avg and max, sigmoid -> sc [B,64].
 // w1 [8][128] indexed by Fcat channel (colour | depth, CODON_x4.py:85), b1 [8], w2 [64][8], b2 [64].
 cudaError_t launch_cac_mlp(const float* part, int chunks, int B, int HW, const float* w1,
                            const float* b1, const float* w2, const float* b2, float* sc,
                            cudaStream_t st);
-// apply: F = F * sc[b, c % 64] * sigmoid(conv5x5(pooled))[b,h,w] + E   (in place on F).
-// ws fp32 [2][25] (max map taps, then mean map taps).
-cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* pooled, const float* sc,
-                             const float* ws, int B, int H, int W, cudaStream_t st, int rnd_tf32 = 0,
-                             int pool_parts = 1,    // 1: pooled = final (max, mean) [B,H,W,2]; 2 / 4: (max, sum) partial maps
-                             size_t part_stride = 0);   // pixels between the partial maps (0: B*H*W)
+// apply: F = F * sc[b, c % 64] * gate[b,h,w] + E   (in place on F).
+cudaError_t launch_cac_apply(void* F, const void* E, int act, const float* gate, const float* sc, int B, int H, int W,
+                             cudaStream_t st, int rnd_tf32 = 0);
 
 // ---- utility -------------------------------------------------------------------------------------
 cudaError_t launch_convert_to_f32(const void* src, int dtype, float* dst, size_t n, cudaStream_t st);
