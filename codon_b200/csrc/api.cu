@@ -573,10 +573,11 @@ int run_forward(codon_ctx* ctx, const float* x, const float* y, float* out, int 
       if (pool_parts == 4 && fj_cstat) {
         // fused conv path: fold the epilogue's per-cell partials (32 B per pixel) instead of re-reading F
         chunks = cac_cell_chunks(bf.cells);
-        ProfScope ps(ctx, PC_CAC_STATS, P * 32, st);
+        // + the gate map computed by the same launch: pool_parts partial maps of 8 B/px in, 4 B/px out
+        ProfScope ps(ctx, PC_CAC_STATS, P * (32 + pool_parts * 8 + 4), st);
         CU_TRY(ctx, launch_cac_cell_reduce(ws + bf.cstat, ws + bf.cstat + bf.cstat_half, B, bf.cells, part, chunks, st, &cg));
       } else {
-        ProfScope ps(ctx, PC_CAC_STATS, P * 128 * r.e, st);
+        ProfScope ps(ctx, PC_CAC_STATS, P * (128 * r.e + pool_parts * 8 + 4), st);
         if (tc_mode) CU_TRY(ctx, launch_cac_chan_stats(ws + bf.F, ctx->act, B, H, W, part, bf.chunks, st));
         else CU_TRY(ctx, launch_cac_stats(ws + bf.F, ctx->act, B, H, W, pooled, part, bf.chunks, st));
         CU_TRY(ctx, launch_cac_gate(cg, B, st));
