@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(RateParams p, unsigned lon
     const uint32_t pitch = (uint32_t)p.sbo;
     const uint32_t sub_off = p.sbo == 1024 ? 16384u : 8u * 128u;     // second sub-tile: next 16 KB / 8 pixels to the right
     int tap = 0, st = 0;
+    uint32_t fused_done = 0;
     t0 = clock64();
     for (int it = 0; it < p.iters; ++it) {
       const int dx = p.shift ? tap % 5 : 0, dy = p.shift ? tap / 5 : 0;
@@ -109,6 +110,44 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(RateParams p, unsigned lon
         if (p.ovh & 16) mbar_wait(rb, 0);
         if (p.ovh & 4) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
+      if (ORDER == 4) {
+        // ONE asm block per issue block (cta_group::2, two accumulators x four K steps + the stage commit).  ovh bit 64:
+        // the phase test of the next stage is the block's FIRST instruction and its result is consumed by the block's
+        // LAST one, so that the poll's latency overlaps the MMA issue; the next iteration waits only if it failed.
+        if (elect_one()) {
+          const uint32_t rb = smem_u32(&bar_ready), cb = smem_u32(&bar_dummy);
+          const uint64_t a0 = ad0, a1 = ad0 + (uint64_t)(sub_off >> 4);
+          const uint32_t d0 = tmem, d1 = tmem + (uint32_t)p.n, acc = it ? 1u : 0u;
+          if (p.ovh & 64) {
+            if (!fused_done) mbar_wait(rb, 0);
+#define MMA4(D, A) \
+            "tcgen05.mma.cta_group::2.kind::f16 [" D "], " A ", %5, %6, p;\n\t" \
+            "add.u64 a, " A ", 2;\n\tadd.u64 b, %5, 2;\n\ttcgen05.mma.cta_group::2.kind::f16 [" D "], a, b, %6, t;\n\t" \
+            "add.u64 a, " A ", 4;\n\tadd.u64 b, %5, 4;\n\ttcgen05.mma.cta_group::2.kind::f16 [" D "], a, b, %6, t;\n\t" \
+            "add.u64 a, " A ", 6;\n\tadd.u64 b, %5, 6;\n\ttcgen05.mma.cta_group::2.kind::f16 [" D "], a, b, %6, t;\n\t"
+            asm volatile("{\n\t.reg .pred q, p, t;\n\t.reg .b64 a, b;\n\t"
+                         "mbarrier.test_wait.parity.shared::cta.b64 q, [%8], %9;\n\t"
+                         "setp.ne.b32 p, %7, 0;\n\tsetp.eq.u32 t, %6, %6;\n\t"
+                         MMA4("%1", "%3") MMA4("%2", "%4")
+                         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%10], %11;\n\t"
+                         "selp.u32 %0, 1, 0, q;\n\t}"
+                         : "=r"(fused_done)
+                         : "r"(d0), "r"(d1), "l"(a0), "l"(a1), "l"(bd), "r"(idesc), "r"(acc), "r"(rb), "r"(0), "r"(cb), "h"((uint16_t)3)
+                         : "memory");
+          } else {
+            asm volatile("{\n\t.reg .pred p, t;\n\t.reg .b64 a, b;\n\t"
+                         "setp.ne.b32 p, %7, 0;\n\tsetp.eq.u32 t, %6, %6;\n\t"
+                         MMA4("%1", "%3") MMA4("%2", "%4")
+                         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%10], %11;\n\t"
+                         "mov.u32 %0, 1;\n\t}"
+                         : "=r"(fused_done)
+                         : "r"(d0), "r"(d1), "l"(a0), "l"(a1), "l"(bd), "r"(idesc), "r"(acc), "r"(rb), "r"(0), "r"(cb), "h"((uint16_t)3)
+                         : "memory");
+#undef MMA4
+          }
+        }
+        __syncwarp();
+      } else
       if (elect_one()) {
 #pragma unroll
         for (int q = 0; q < 4 * NACC; ++q) {
@@ -264,6 +303,16 @@ int main(int argc, char** argv) {
         p.ovh = ovh;
         snprintf(label, sizeof label, "cg2 N128 4 MMAs/block %s ovh %2d (x4 = cyc/block)", with_mma ? "MMA " : "none", ovh);
         rc |= with_mma ? run<2, 1, 0>(label, p, sms & ~1, d_out) : run<2, 1, 3>(label, p, sms & ~1, d_out);
+      }
+    // one asm block per issue block, without / with the next stage's phase test fused into it
+    for (int n : {64, 128})
+      for (int ovh : {0, 64}) {
+        char label[160];
+        RateParams p = {};
+        p.n = n; p.m = 256; p.b_rows = n / 2; p.sbo = 2560; p.shift = 1; p.commit_each = 0; p.data = 2; p.nacc = 2; p.iters = iters;
+        p.ovh = ovh;
+        snprintf(label, sizeof label, "cg2 N%d 8 MMAs in ONE asm block, test %s (x8 = cyc/block)", n, ovh ? "fused" : "none ");
+        rc |= run<2, 2, 4>(label, p, sms & ~1, d_out);
       }
     // the same with N = 64 blocks of 8 MMAs (pair kernel border taps: 344 cycles of tensor work per block)
     for (int ovh : {0, 2, 2 | 4, 2 | 4 | 8 | 16, 1 | 2 | 32 | 4 | 8 | 16}) {
